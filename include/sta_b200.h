@@ -1,0 +1,152 @@
+/*
+ * sta_b200.h -- C ABI of libsta_b200.so, the B200 (sm_100a) implementation of the
+ * ViSTA-SLAM "Symmetric Two-view Association" (STA) frontend forward pass.
+ *
+ * The library is the drop-in boundary underneath the reference's Python module
+ * vista_slam/sta_model/sta_model.py::SymmetricTwoViewAssociation.  Every model-level
+ * entry point below names the reference method it replaces (file:line in
+ * zhangganlin/vista-slam).  Conventions:
+ *   - plain C: pointers, sizes, opaque handle; no C++/torch types, no exceptions;
+ *   - every function returns 0 on success, non-zero on failure; sta_last_error()
+ *     then returns a thread-local human-readable message;
+ *   - all "dev" pointers are CUDA device pointers on the current device, "host"
+ *     pointers are host memory; `stream` is a cudaStream_t passed as void* (NULL =
+ *     default stream); calls are asynchronous with respect to the host unless noted;
+ *   - the caller owns all input/output buffers, the handle owns weights + workspace;
+ *   - the CUDA kernels are the only implementation: there is no CPU fallback.
+ */
+#ifndef STA_B200_H_
+#define STA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct StaModel StaModel; /* opaque */
+
+/* ---- library ---- */
+const char* sta_last_error(void);
+int sta_version(void);                 /* ABI version, currently 1 */
+int sta_device_synchronize(void);      /* cudaDeviceSynchronize + error check */
+
+/* ---- model lifetime (replaces STA() + load_state_dict + .to(cuda), slam.py:95-106) ---- */
+int sta_create(StaModel** out);
+void sta_destroy(StaModel* m);
+
+/* Upload one state-dict tensor (fp32, contiguous, host or device memory) under its
+ * reference state_dict name (e.g. "enc_blocks.0.attn.qkv.weight").
+ * The library converts/packs it into its own bf16 / fp32 device layout.
+ * Names the forward pass does not use (enc_norm.*, refinenet4.resConfUnit1.*, the
+ * aliased scratch.layerN_rn.*) are accepted and ignored.  Returns non-zero for an
+ * unknown name or a shape mismatch (strict=True semantics, sta_model.py:143). */
+int sta_load_tensor(StaModel* m, const char* name, const float* data, const int64_t* shape, int ndim,
+                    int data_on_device);
+/* Number of tensors still missing before the model can run (0 = ready). */
+int sta_missing_tensors(StaModel* m);
+/* The packed weights live in ONE device arena.  For multi-GPU runs rank 0 loads the state dict,
+ * every rank exposes its arena, the host broadcasts it (torch.distributed / ncclBroadcast over NVLink)
+ * and the receiving ranks call sta_mark_all_loaded. */
+int sta_weight_arena(StaModel* m, void** dev_ptr_out, int64_t* bytes_out);
+int sta_mark_all_loaded(StaModel* m);
+
+/* ---- model-level forward entry points ---- */
+
+/* _encode_image(image, true_shape, normalize=False), sta_model.py:163-174.
+ * img_dev: [B,3,H,W] fp32 (img_is_bf16 = 0) or bf16 (1), values in [-1,1].
+ * feat_out_dev: [B, (H/16)*(W/16), 1024] fp32.  pos_out_dev: [B, N, 2] int64 (y, x) or NULL. */
+int sta_encode(StaModel* m, const void* img_dev, int img_is_bf16, int B, int H, int W, float* feat_out_dev,
+               int64_t* pos_out_dev, void* stream);
+
+/* _decode_stereo(feat1, feat2, pos1, pos2), sta_model.py:177-244.
+ * feat*_dev: [B,N,1024] fp32; pos*_dev: [B,N,2] int64 (values in [-1,1023]).
+ * out1_dev / out2_dev: arrays (host memory) of 13 device pointers, each [B,N+1,768] fp32 or NULL to
+ * skip that layer's output; entry 12 is LayerNorm-ed (dec_norm), as in the reference. */
+int sta_decode(StaModel* m, const float* feat1_dev, const float* feat2_dev, const int64_t* pos1_dev,
+               const int64_t* pos2_dev, int B, int N, float* const* out1_dev, float* const* out2_dev, void* stream);
+
+/* head_pose_s(tok), heads/pose_head.py:109-119.  tok_dev: [B,768] fp32 (already dec_norm-ed).
+ * pose_out_dev: [B,4,4] fp32, conf_out_dev: [B] fp32. */
+int sta_head_pose(StaModel* m, const float* tok_dev, int B, float* pose_out_dev, float* conf_out_dev, void* stream);
+
+/* head_pts([enc_feat] + [dec_k[:,1:]]_k, true_shape), sta_model.py:135-137 + utils/misc.py:48-76 +
+ * heads/dpt_head.py:34-66.  Only the four hooked layers are read:
+ *   enc_feat_dev [B,N,1024], dec6_dev, dec9_dev, dec12_dev [B,N,768] fp32 (pose token already dropped).
+ * pts3d_out_dev: [B,H,W,3] fp32, conf_out_dev: [B,H,W] fp32. */
+int sta_head_pts(StaModel* m, const float* enc_feat_dev, const float* dec6_dev, const float* dec9_dev,
+                 const float* dec12_dev, int B, int H, int W, float* pts3d_out_dev, float* conf_out_dev,
+                 void* stream);
+
+/* forward(views) for ONE support view over a batch of B pairs (sta_model.py:247-291): 2 encodes +
+ * symmetric decode + 2 DPT heads + 2 pose heads, fused fast path (no per-layer outputs).
+ * img1 = main view, img2 = support view, each [B,3,H,W].  Outputs, index 0 = main view, 1 = support:
+ * pts3d_out_dev [2,B,H,W,3], conf_out_dev [2,B,H,W], pose_out_dev [2,B,4,4], pose_conf_out_dev [2,B]. */
+int sta_forward_pairs(StaModel* m, const void* img1_dev, const void* img2_dev, int img_is_bf16, int B, int H, int W,
+                      float* pts3d_out_dev, float* conf_out_dev, float* pose_out_dev, float* pose_conf_out_dev,
+                      void* stream);
+
+/* Same as sta_forward_pairs but with HOST buffers (pinned or pageable): copies the images to the
+ * device, runs the forward, copies the four outputs back and synchronises the stream.
+ * This is the end-to-end entry point bench.py times as "e2e". */
+int sta_forward_pairs_host(StaModel* m, const void* img1_host, const void* img2_host, int img_is_bf16, int B, int H,
+                           int W, float* pts3d_out_host, float* conf_out_host, float* pose_out_host,
+                           float* pose_conf_out_host, void* stream);
+
+/* Counters: number of kernel launches issued by this library on behalf of `m` since creation. */
+int64_t sta_launch_count(StaModel* m);
+/* Bytes of device memory currently held (weights + workspace). */
+int64_t sta_device_bytes(StaModel* m);
+
+/* ---- op-level entry points (used by the parity tests; same kernels the model uses) ---- */
+
+enum { STA_EPI_BF16 = 0, STA_EPI_GELU = 1, STA_EPI_F32 = 2, STA_EPI_ROPE = 3, STA_EPI_PIXSHUF = 4, STA_EPI_HEAD = 5 };
+
+typedef struct StaGemmDesc {
+  int conv3x3;          /* 0: A is [M][lda] bf16;  1: A is NHWC [nimg][H][W][Cin] bf16 (3x3, pad 1, stride 1) */
+  int epi;              /* STA_EPI_* */
+  const void* A;
+  int64_t lda;
+  const void* W;        /* [N][ldw] bf16; for conv3x3 K = 9*Cin ordered (kh, kw, cin) */
+  int64_t ldw;
+  int M, N, K;
+  int nimg, H, Wd, Cin; /* conv3x3 geometry */
+  const float* bias;    /* [N] fp32 or NULL */
+  void* out;            /* bf16 (EPI_BF16/GELU/ROPE/PIXSHUF) or fp32 (EPI_F32) */
+  int64_t ldo;
+  void* out2;           /* EPI_BF16: optional relu copy */
+  const void* resid;    /* EPI_BF16: bf16 [.][ldo];  EPI_F32: fp32 [.][ldo] */
+  const void* resid2;   /* EPI_BF16 only */
+  int relu_main;
+  int rowmap_n;         /* EPI_F32: insert one skipped row before every n output rows */
+  const int32_t* pos;   /* EPI_ROPE: [M][2] int32 (y, x) */
+  int rope_cols;        /* EPI_ROPE: columns [0, rope_cols) are rotated */
+  int ps_k, ps_cout, ps_h, ps_w; /* EPI_PIXSHUF */
+  const float* head_w;  /* EPI_HEAD: [128][4] fp32 */
+  const float* head_b;  /* EPI_HEAD: [4] */
+  float* pts3d;         /* EPI_HEAD: [pixels][3] */
+  float* conf;          /* EPI_HEAD: [pixels] */
+} StaGemmDesc;
+
+int sta_op_gemm(const StaGemmDesc* d, void* stream);
+
+/* softmax(q k^T * scale) v, head_dim 64.  q/k/v: [batch][n*][ld*] bf16 with head h at columns
+ * *_col0 + 64*h; out: [batch][nq][ldo] bf16.  kv sample for query sample b is (b + kv_batch_shift) % batch. */
+int sta_op_attention(const void* q, int64_t ldq, int q_col0, const void* k, int64_t ldk, int k_col0, const void* v,
+                     int64_t ldv, int v_col0, void* out, int64_t ldo, int batch, int heads, int nq, int nk,
+                     int kv_batch_shift, float scale, void* stream);
+
+int sta_op_layernorm(const float* x, int rows, int C, float eps, const float* g1, const float* b1, void* out1_bf16,
+                     const float* g2, const float* b2, void* out2_bf16, int drop_first_of, void* stream);
+int sta_op_patch_im2col(const void* img, int img_is_bf16, int B, int H, int W, void* out_bf16, void* stream);
+int sta_op_upsample2x(const void* in_bf16, void* out_bf16, int nimg, int H, int W, int C, void* stream);
+int sta_op_im2col_3x3_s2(const void* in_bf16, void* out_bf16, int nimg, int H, int W, int C, void* stream);
+int sta_op_cast_f32_bf16(const float* in, void* out_bf16, int64_t rows, int C, int drop_first_of, void* stream);
+/* In-place 2-D RoPE on tokens [B][N][H][64] bf16 with int64 positions [B][N][2]: the contract of
+ * curope.rope_2d (pos_embed/curope/curope.cpp:49-65, kernels.cu:84-108), base 100, F0 = 1. */
+int sta_op_rope2d(void* tokens_bf16, const int64_t* pos, int B, int N, int H, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STA_B200_H_ */

@@ -1,0 +1,339 @@
+"""GPU bring-up of the op-level kernels against plain torch fp32 references (run under gpurun).
+
+    python tools/bringup.py            # runs every group in its own subprocess (a trap kills only that group)
+    python tools/bringup.py <group>    # run one group in-process
+
+Prints one line per check: name, max abs err, max ref magnitude, PASS/FAIL.
+"""
+import math
+import os
+import subprocess
+import sys
+import time
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+GROUPS = ["gemm_basic", "gemm_epi", "conv", "attention", "misc", "perf"]
+
+
+def report(name, got, ref, tol):
+    import torch
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs().max().item()
+    mag = ref.abs().max().item()
+    bad = not math.isfinite(err) or err > tol * max(mag, 1e-6)
+    print("%-44s err=%.3e ref_max=%.3e rel=%.2e %s" % (name, err, mag, err / max(mag, 1e-12), "FAIL" if bad else "PASS"),
+          flush=True)
+    return not bad
+
+
+def gemm_desc(**kw):
+    from vista_slam_b200._lib import StaGemmDesc
+    d = StaGemmDesc()
+    for k, v in kw.items():
+        if hasattr(v, "data_ptr"):
+            v = v.data_ptr()
+        setattr(d, k, v)
+    return d
+
+
+def run_gemm(d):
+    import ctypes
+    from vista_slam_b200._lib import check, cur_stream, lib
+    check(lib().sta_op_gemm(ctypes.byref(d), cur_stream()), "sta_op_gemm")
+
+
+def group_gemm_basic():
+    import torch
+    from vista_slam_b200._lib import EPI_BF16
+    torch.manual_seed(0)
+    dev = "cuda"
+    for (M, N, K) in [(128, 256, 64), (300, 512, 192), (128, 256, 1024), (8192, 1024, 1024), (1000, 384, 768),
+                      (24608, 768, 768)]:
+        A = torch.randn(M, K, device=dev).bfloat16()
+        W = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+        bias = torch.randn(N, device=dev)
+        out = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+        d = gemm_desc(conv3x3=0, epi=EPI_BF16, A=A, lda=K, W=W, ldw=K, M=M, N=N, K=K, bias=bias, out=out, ldo=N)
+        run_gemm(d)
+        torch.cuda.synchronize()
+        ref = A.float() @ W.float().t() + bias
+        report("gemm bf16 M%d N%d K%d" % (M, N, K), out, ref, 1e-2)
+
+
+def rope_ref(x, pos):
+    """x: [rows, heads, 64] fp32, pos: [rows, 2] -> rotated (pos_embed.py:149-185 semantics)."""
+    import torch
+    inv = 1.0 / (100.0 ** (torch.arange(16, device=x.device, dtype=torch.float32) / 16))
+    out = x.clone()
+    for axis in range(2):
+        ang = pos[:, axis].float()[:, None] * inv[None, :]
+        cos = ang.cos()[:, None, :]
+        sin = ang.sin()[:, None, :]
+        a = x[..., axis * 32: axis * 32 + 16]
+        b = x[..., axis * 32 + 16: axis * 32 + 32]
+        out[..., axis * 32: axis * 32 + 16] = a * cos - b * sin
+        out[..., axis * 32 + 16: axis * 32 + 32] = b * cos + a * sin
+    return out
+
+
+def group_gemm_epi():
+    import torch
+    import torch.nn.functional as F
+    from vista_slam_b200._lib import EPI_BF16, EPI_F32, EPI_GELU, EPI_PIXSHUF, EPI_ROPE
+    torch.manual_seed(1)
+    dev = "cuda"
+    M, N, K = 777, 512, 256
+    A = torch.randn(M, K, device=dev).bfloat16()
+    W = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev)
+    base = A.float() @ W.float().t() + bias
+    # GELU
+    out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    run_gemm(gemm_desc(epi=EPI_GELU, A=A, lda=K, W=W, ldw=K, M=M, N=N, K=K, bias=bias, out=out, ldo=N))
+    report("epi gelu", out, F.gelu(base), 1e-2)
+    # BF16 + resid + resid2 + relu copy
+    r1 = torch.randn(M, N, device=dev).bfloat16()
+    r2 = torch.randn(M, N, device=dev).bfloat16()
+    out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    out2 = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    run_gemm(gemm_desc(epi=EPI_BF16, A=A, lda=K, W=W, ldw=K, M=M, N=N, K=K, bias=bias, out=out, ldo=N, out2=out2,
+                       resid=r1, resid2=r2))
+    ref = base + r1.float() + r2.float()
+    report("epi bf16 resid x2", out, ref, 1e-2)
+    report("epi bf16 relu copy", out2, ref.relu(), 1e-2)
+    out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    run_gemm(gemm_desc(epi=EPI_BF16, A=A, lda=K, W=W, ldw=K, M=M, N=N, K=K, bias=bias, out=out, ldo=N, relu_main=1))
+    report("epi bf16 relu main", out, base.relu(), 1e-2)
+    # N = 384 -> BN 128 path
+    W3 = (torch.randn(384, K, device=dev) / math.sqrt(K)).bfloat16()
+    out = torch.zeros(M, 384, device=dev, dtype=torch.bfloat16)
+    run_gemm(gemm_desc(epi=EPI_BF16, A=A, lda=K, W=W3, ldw=K, M=M, N=384, K=K, out=out, ldo=384))
+    report("epi bf16 N384 (BN128, no bias)", out, A.float() @ W3.float().t(), 1e-2)
+    # F32 with residual in place
+    x = torch.randn(M, N, device=dev)
+    x0 = x.clone()
+    run_gemm(gemm_desc(epi=EPI_F32, A=A, lda=K, W=W, ldw=K, M=M, N=N, K=K, bias=bias, out=x, ldo=N, resid=x))
+    report("epi f32 resid in place", x, x0 + base, 2e-3)
+    # F32 with rowmap (decoder_embed): 7 samples x 111 tokens
+    nt = 111
+    xd = torch.zeros(7 * (nt + 1), N, device=dev)
+    run_gemm(gemm_desc(epi=EPI_F32, A=A, lda=K, W=W, ldw=K, M=M, N=N, K=K, bias=bias, out=xd, ldo=N, rowmap_n=nt))
+    ref = torch.zeros(7, nt + 1, N, device=dev)
+    ref[:, 1:] = base.view(7, nt, N)
+    report("epi f32 rowmap", xd, ref.view(-1, N), 2e-3)
+    # ROPE: N = 3*256 (4 heads), rope on first 512 columns, positions incl. -1
+    C = 256
+    Wq = (torch.randn(3 * C, K, device=dev) / math.sqrt(K)).bfloat16()
+    bq = torch.randn(3 * C, device=dev)
+    pos = torch.randint(-1, 40, (M, 2), device=dev, dtype=torch.int32)
+    out = torch.zeros(M, 3 * C, device=dev, dtype=torch.bfloat16)
+    run_gemm(gemm_desc(epi=EPI_ROPE, A=A, lda=K, W=Wq, ldw=K, M=M, N=3 * C, K=K, bias=bq, out=out, ldo=3 * C, pos=pos,
+                       rope_cols=2 * C))
+    qkv = A.float() @ Wq.float().t() + bq
+    ref = qkv.clone()
+    ref[:, :2 * C] = rope_ref(qkv[:, :2 * C].reshape(M, 8, 64), pos).reshape(M, 2 * C)
+    report("epi rope", out, ref, 1e-2)
+    # PIXSHUF: tokens (2 img, 5x7 grid), Cin 128, cout 64, k 2
+    nimg, h, w, cin, cout, k = 2, 5, 7, 128, 64, 2
+    At = torch.randn(nimg * h * w, cin, device=dev).bfloat16()
+    Wt = (torch.randn(cin, cout, k, k, device=dev) / math.sqrt(cin))  # ConvTranspose2d weight layout
+    bt = torch.randn(cout, device=dev)
+    Wp = Wt.permute(2, 3, 1, 0).reshape(k * k * cout, cin).contiguous().bfloat16()
+    out = torch.zeros(nimg, h * k, w * k, cout, device=dev, dtype=torch.bfloat16)
+    run_gemm(gemm_desc(epi=EPI_PIXSHUF, A=At, lda=cin, W=Wp, ldw=cin, M=nimg * h * w, N=k * k * cout, K=cin, bias=bt,
+                       out=out, ps_k=k, ps_cout=cout, ps_h=h, ps_w=w))
+    xin = At.float().view(nimg, h, w, cin).permute(0, 3, 1, 2)
+    ref = F.conv_transpose2d(xin, Wp.float().view(k, k, cout, cin).permute(3, 2, 0, 1), bt, stride=k)
+    report("epi pixshuf (ConvTranspose k=s)", out, ref.permute(0, 2, 3, 1), 1e-2)
+    torch.cuda.synchronize()
+
+
+def group_conv():
+    import torch
+    import torch.nn.functional as F
+    from vista_slam_b200._lib import EPI_BF16, EPI_HEAD
+    torch.manual_seed(2)
+    dev = "cuda"
+    for (nimg, H, W, Cin, Cout) in [(2, 8, 16, 64, 256), (3, 14, 14, 128, 256), (2, 24, 32, 256, 256),
+                                    (1, 20, 36, 256, 128)]:
+        x = torch.randn(nimg, H, W, Cin, device=dev).bfloat16()
+        wt = (torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(9 * Cin))
+        b = torch.randn(Cout, device=dev)
+        wp = wt.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous().bfloat16()
+        r1 = torch.randn(nimg, H, W, Cout, device=dev).bfloat16()
+        out = torch.zeros(nimg, H, W, Cout, device=dev, dtype=torch.bfloat16)
+        out2 = torch.zeros_like(out)
+        run_gemm(gemm_desc(conv3x3=1, epi=EPI_BF16, A=x, W=wp, ldw=9 * Cin, N=Cout, K=9 * Cin, nimg=nimg, H=H, Wd=W,
+                           Cin=Cin, bias=b, out=out, ldo=Cout, out2=out2, resid=r1))
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), wp.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2), b,
+                       padding=1).permute(0, 2, 3, 1) + r1.float()
+        report("conv3x3 %dx%dx%d C%d->%d" % (nimg, H, W, Cin, Cout), out, ref, 1e-2)
+        report("   relu copy", out2, ref.relu(), 1e-2)
+    # head: conv 128->128 + relu + 1x1 (128->4) + postprocess
+    nimg, H, W = 2, 32, 48
+    x = torch.randn(nimg, H, W, 128, device=dev).bfloat16()
+    wt = torch.randn(128, 128, 3, 3, device=dev) / math.sqrt(9 * 128)
+    b = torch.randn(128, device=dev) * 0.1
+    wp = wt.permute(0, 2, 3, 1).reshape(128, 9 * 128).contiguous().bfloat16()
+    w4 = torch.randn(4, 128, device=dev) / math.sqrt(128)
+    b4 = torch.randn(4, device=dev) * 0.1
+    w4t = w4.t().contiguous()
+    pts = torch.zeros(nimg, H, W, 3, device=dev)
+    conf = torch.zeros(nimg, H, W, device=dev)
+    run_gemm(gemm_desc(conv3x3=1, epi=EPI_HEAD, A=x, W=wp, ldw=9 * 128, N=128, K=9 * 128, nimg=nimg, H=H, Wd=W, Cin=128,
+                       bias=b, head_w=w4t, head_b=b4, pts3d=pts, conf=conf))
+    hid = F.conv2d(x.float().permute(0, 3, 1, 2), wp.float().view(128, 3, 3, 128).permute(0, 3, 1, 2), b,
+                   padding=1).relu()
+    o = torch.einsum("nchw,oc->nhwo", hid, w4) + b4
+    xyz = o[..., :3]
+    dd = xyz.norm(dim=-1, keepdim=True)
+    ref_pts = xyz / dd.clip(min=1e-8) * torch.expm1(dd)
+    ref_conf = 1 + o[..., 3].exp()
+    report("head conv+1x1+postprocess pts3d", pts, ref_pts, 5e-3)
+    report("head conv+1x1+postprocess conf", conf, ref_conf, 5e-3)
+    torch.cuda.synchronize()
+
+
+def group_attention():
+    import torch
+    import torch.nn.functional as F
+    from vista_slam_b200._lib import check, cur_stream, lib, ptr
+    torch.manual_seed(3)
+    dev = "cuda"
+    L = lib()
+    for (batch, heads, n, shift) in [(2, 3, 128, 0), (2, 3, 196, 0), (2, 12, 769, 0), (4, 12, 769, 2), (3, 16, 768, 0)]:
+        C = heads * 64
+        qkv = torch.randn(batch, n, 3 * C, device=dev).bfloat16()
+        out = torch.zeros(batch, n, C, device=dev, dtype=torch.bfloat16)
+        check(L.sta_op_attention(ptr(qkv), 3 * C, 0, ptr(qkv), 3 * C, C, ptr(qkv), 3 * C, 2 * C, ptr(out), C, batch,
+                                 heads, n, n, shift, 0.125, cur_stream()), "attention")
+        torch.cuda.synchronize()
+        q, k, v = [qkv[..., i * C:(i + 1) * C].float().view(batch, n, heads, 64).transpose(1, 2) for i in range(3)]
+        if shift:
+            idx = [(b + shift) % batch for b in range(batch)]
+            k, v = k[idx], v[idx]
+        ref = F.scaled_dot_product_attention(q, k, v, scale=0.125).transpose(1, 2).reshape(batch, n, C)
+        report("attention b%d h%d n%d shift%d" % (batch, heads, n, shift), out, ref, 2e-2)
+
+
+def group_misc():
+    import torch
+    import torch.nn.functional as F
+    from vista_slam_b200._lib import check, cur_stream, lib, ptr
+    torch.manual_seed(4)
+    dev = "cuda"
+    L = lib()
+    st = cur_stream()
+    for C in (768, 1024):
+        rows = 1000
+        x = torch.randn(rows, C, device=dev) * 3 + 0.5
+        g1, b1, g2, b2 = [torch.randn(C, device=dev) for _ in range(4)]
+        o1 = torch.zeros(rows, C, device=dev, dtype=torch.bfloat16)
+        o2 = torch.zeros_like(o1)
+        check(L.sta_op_layernorm(ptr(x), rows, C, 1e-6, ptr(g1), ptr(b1), ptr(o1), ptr(g2), ptr(b2), ptr(o2), 0, st))
+        report("layernorm C%d out1" % C, o1, F.layer_norm(x, (C,), g1, b1, 1e-6), 1e-2)
+        report("layernorm C%d out2" % C, o2, F.layer_norm(x, (C,), g2, b2, 1e-6), 1e-2)
+    # drop_first_of
+    x = torch.randn(4 * 51, 768, device=dev)
+    g1, b1 = torch.randn(768, device=dev), torch.randn(768, device=dev)
+    o1 = torch.zeros(4 * 50, 768, device=dev, dtype=torch.bfloat16)
+    check(L.sta_op_layernorm(ptr(x), 4 * 51, 768, 1e-6, ptr(g1), ptr(b1), ptr(o1), None, None, None, 51, st))
+    report("layernorm drop pose row", o1, F.layer_norm(x, (768,), g1, b1, 1e-6).view(4, 51, 768)[:, 1:].reshape(-1, 768),
+           1e-2)
+    # patch im2col
+    img = torch.rand(2, 3, 32, 48, device=dev) * 2 - 1
+    o = torch.zeros(2 * 2 * 3, 768, device=dev, dtype=torch.bfloat16)
+    check(L.sta_op_patch_im2col(ptr(img), 0, 2, 32, 48, ptr(o), st))
+    ref = F.unfold(img, 16, stride=16).transpose(1, 2).reshape(-1, 768)
+    report("patch im2col fp32", o, ref, 1e-2)
+    imgb = img.bfloat16()
+    check(L.sta_op_patch_im2col(ptr(imgb), 1, 2, 32, 48, ptr(o), st))
+    report("patch im2col bf16", o, F.unfold(imgb.float(), 16, stride=16).transpose(1, 2).reshape(-1, 768), 1e-6)
+    # upsample
+    x = torch.randn(2, 7, 9, 64, device=dev).bfloat16()
+    o = torch.zeros(2, 14, 18, 64, device=dev, dtype=torch.bfloat16)
+    check(L.sta_op_upsample2x(ptr(x), ptr(o), 2, 7, 9, 64, st))
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True)
+    report("upsample2x align_corners", o, ref.permute(0, 2, 3, 1), 1e-2)
+    # im2col s2
+    x = torch.randn(2, 7, 10, 64, device=dev).bfloat16()
+    o = torch.zeros(2 * 4 * 5, 9 * 64, device=dev, dtype=torch.bfloat16)
+    check(L.sta_op_im2col_3x3_s2(ptr(x), ptr(o), 2, 7, 10, 64, st))
+    ref = F.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)  # [n, C*9, L] with (c, tap) order
+    ref = ref.view(2, 64, 9, -1).permute(0, 3, 2, 1).reshape(-1, 9 * 64)
+    report("im2col 3x3 s2", o, ref, 1e-6)
+    # cast with drop
+    x = torch.randn(3 * 11, 768, device=dev)
+    o = torch.zeros(3 * 10, 768, device=dev, dtype=torch.bfloat16)
+    check(L.sta_op_cast_f32_bf16(ptr(x), ptr(o), 33, 768, 11, st))
+    report("cast drop", o, x.view(3, 11, 768)[:, 1:].reshape(-1, 768), 1e-2)
+    # rope2d op
+    tok = torch.randn(2, 50, 4, 64, device=dev).bfloat16()
+    pos = torch.randint(-1, 30, (2, 50, 2), device=dev, dtype=torch.int64)
+    ref = rope_ref(tok.float().view(100, 4, 64), pos.view(100, 2))
+    check(L.sta_op_rope2d(ptr(tok), ptr(pos), 2, 50, 4, st))
+    report("rope2d op", tok.view(100, 4, 64), ref, 1e-2)
+    torch.cuda.synchronize()
+
+
+def group_perf():
+    import torch
+    from vista_slam_b200._lib import EPI_BF16, EPI_GELU, check, cur_stream, lib, ptr
+    dev = "cuda"
+    torch.manual_seed(5)
+
+    def timeit(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for (M, N, K, epi) in [(24576, 3072, 1024, EPI_BF16), (24576, 4096, 1024, EPI_GELU), (24576, 1024, 4096, EPI_BF16),
+                           (24576, 1024, 1024, EPI_BF16)]:
+        A = torch.randn(M, K, device=dev).bfloat16()
+        W = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+        bias = torch.randn(N, device=dev)
+        out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+        d = gemm_desc(epi=epi, A=A, lda=K, W=W, ldw=K, M=M, N=N, K=K, bias=bias, out=out, ldo=N)
+        ms = timeit(lambda: run_gemm(d))
+        ms_t = timeit(lambda: torch.matmul(A, W.t()))
+        print("gemm M%d N%d K%d epi%d: %.3f ms = %.0f TFLOP/s   (torch.matmul %.3f ms = %.0f TFLOP/s)" %
+              (M, N, K, epi, ms, 2.0 * M * N * K / ms / 1e9, ms_t, 2.0 * M * N * K / ms_t / 1e9), flush=True)
+    L = lib()
+    for (batch, heads, n) in [(32, 16, 768), (32, 12, 769)]:
+        C = heads * 64
+        qkv = torch.randn(batch, n, 3 * C, device=dev).bfloat16()
+        out = torch.zeros(batch, n, C, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda: check(L.sta_op_attention(ptr(qkv), 3 * C, 0, ptr(qkv), 3 * C, C, ptr(qkv), 3 * C, 2 * C,
+                                                     ptr(out), C, batch, heads, n, n, 0, 0.125, cur_stream())))
+        fl = 4.0 * batch * heads * n * n * 64
+        print("attention b%d h%d n%d: %.3f ms = %.0f TFLOP/s" % (batch, heads, n, ms, fl / ms / 1e9), flush=True)
+
+
+def main():
+    if len(sys.argv) > 1:
+        import torch
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        globals()["group_" + sys.argv[1]]()
+        return
+    for g in GROUPS:
+        print("=== group %s ===" % g, flush=True)
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), g], timeout=300)
+            print("=== group %s exit %d (%.1fs) ===" % (g, r.returncode, time.time() - t0), flush=True)
+        except subprocess.TimeoutExpired:
+            print("=== group %s TIMEOUT ===" % g, flush=True)
+
+
+if __name__ == "__main__":
+    main()

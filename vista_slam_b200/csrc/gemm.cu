@@ -1,0 +1,84 @@
+// Host launcher for the tcgen05 GEMM / implicit-GEMM convolution (gemm.cuh).
+#include "gemm.cuh"
+#include "host_util.h"
+#include "ops.h"
+
+namespace sta {
+
+template <int BN, int AMODE, int EPI>
+static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_tiles,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_tc_kernel<BN, AMODE, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    STA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  if (grid < 1) return 0;
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  STA_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
+  GemmParams p = g.p;
+  STA_REQUIRE(p.N % 32 == 0, "N must be a multiple of 32");
+  STA_REQUIRE(g.A != nullptr && g.Wt != nullptr, "null operand");
+  STA_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.Wt) & 15) == 0,
+              "operands must be 16-byte aligned");
+
+  // BN = 256 for the wide trunk layers, 128 when N is not a multiple of 256.
+  const int bn = (p.N % 256 == 0 && g.epi != EPI_PIXSHUF && g.epi != EPI_HEAD) ? 256 : 128;
+
+  CUtensorMap tmA, tmB;
+  int m_tiles;
+  if (g.amode == A_CONV3) {
+    STA_REQUIRE(p.Cin % 64 == 0, "conv input channels must be a multiple of 64");
+    STA_REQUIRE(p.K == 9 * p.Cin, "conv K must be 9*Cin");
+    p.tiles_h = (p.H + 7) / 8;
+    p.tiles_w = (p.W + 15) / 16;
+    p.M = p.nimg * p.H * p.W;
+    m_tiles = p.nimg * p.tiles_h * p.tiles_w;
+    uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.nimg};
+    uint64_t strides[3] = {(uint64_t)p.Cin * 2, (uint64_t)p.W * p.Cin * 2, (uint64_t)p.H * p.W * p.Cin * 2};
+    uint32_t box[4] = {64, 16, 8, 1};
+    if (make_tmap_bf16(&tmA, g.A, 4, dims, strides, box)) return 1;
+  } else {
+    STA_REQUIRE(g.lda % 8 == 0, "lda must be a multiple of 8 elements (16 bytes)");
+    m_tiles = (p.M + 127) / 128;
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M};
+    uint64_t strides[1] = {(uint64_t)g.lda * 2};
+    uint32_t box[2] = {64, 128};
+    if (make_tmap_bf16(&tmA, g.A, 2, dims, strides, box)) return 1;
+  }
+  {
+    STA_REQUIRE(g.ldw % 8 == 0, "ldw must be a multiple of 8 elements (16 bytes)");
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+    uint64_t strides[1] = {(uint64_t)g.ldw * 2};
+    uint32_t box[2] = {64, (uint32_t)bn};
+    if (make_tmap_bf16(&tmB, g.Wt, 2, dims, strides, box)) return 1;
+  }
+  const int n_tiles = (p.N + bn - 1) / bn;
+  const int num_tiles = m_tiles * n_tiles;
+
+#define STA_GEMM_CASE(BN_, AM_, EP_) \
+  if (bn == BN_ && g.amode == AM_ && g.epi == EP_) return launch_inst<BN_, AM_, EP_>(tmA, tmB, p, num_tiles, stream);
+
+  STA_GEMM_CASE(256, A_LINEAR, EPI_BF16)
+  STA_GEMM_CASE(256, A_LINEAR, EPI_GELU)
+  STA_GEMM_CASE(256, A_LINEAR, EPI_F32)
+  STA_GEMM_CASE(256, A_LINEAR, EPI_ROPE)
+  STA_GEMM_CASE(128, A_LINEAR, EPI_BF16)
+  STA_GEMM_CASE(128, A_LINEAR, EPI_F32)
+  STA_GEMM_CASE(128, A_LINEAR, EPI_PIXSHUF)
+  STA_GEMM_CASE(256, A_CONV3, EPI_BF16)
+  STA_GEMM_CASE(128, A_CONV3, EPI_BF16)
+  STA_GEMM_CASE(128, A_CONV3, EPI_HEAD)
+#undef STA_GEMM_CASE
+  set_last_error("launch_gemm: unsupported (BN, amode, epilogue) combination");
+  return 2;
+}
+
+}  // namespace sta

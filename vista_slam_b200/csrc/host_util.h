@@ -1,0 +1,48 @@
+// Host-side helpers: error reporting for the C-ABI, TMA tensor-map encoding.
+// libcuda is NOT linked: cuTensorMapEncodeTiled is resolved at run time through
+// cudaGetDriverEntryPoint so the library loads (and exports its symbols) on a
+// machine without a GPU driver.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace sta {
+
+void set_last_error(const std::string& msg);
+const char* get_last_error();
+
+#define STA_CHECK_CUDA(expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      char _buf[512];                                                                             \
+      snprintf(_buf, sizeof(_buf), "%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,             \
+               cudaGetErrorString(_e));                                                           \
+      sta::set_last_error(_buf);                                                                  \
+      return 1;                                                                                   \
+    }                                                                                             \
+  } while (0)
+
+#define STA_REQUIRE(cond, msg)                                                                    \
+  do {                                                                                            \
+    if (!(cond)) {                                                                                \
+      char _buf[512];                                                                             \
+      snprintf(_buf, sizeof(_buf), "%s:%d: requirement failed: %s (%s)", __FILE__, __LINE__,      \
+               #cond, msg);                                                                       \
+      sta::set_last_error(_buf);                                                                  \
+      return 2;                                                                                   \
+    }                                                                                             \
+  } while (0)
+
+// Encode a tiled bf16 tensor map with 128-byte swizzle.  dims[0] is the innermost
+// (contiguous) dimension; strides_bytes[i] is the byte stride of dims[i+1].
+// Returns 0 on success.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box);
+
+int num_sms();
+
+}  // namespace sta

@@ -1,0 +1,1141 @@
+// STA model runtime: packed weights, workspace and the kernel sequence of the forward pass,
+// exported through the C ABI declared in include/sta_b200.h.
+//
+// Mirrors (behaviour, not code) vista_slam/sta_model/sta_model.py:
+//   _encode_image :163-174, _decode_stereo :177-244, forward :247-291,
+//   DPT head heads/dpt_head.py:34-66 + heads/dpt_block.py, pose head heads/pose_head.py:109-119.
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/sta_b200.h"
+#include "host_util.h"
+#include "ops.h"
+
+namespace sta {
+
+// ---------------------------------------------------------------------------
+// weight packing kernels (run once per tensor at load time)
+// ---------------------------------------------------------------------------
+// dst[r * ldd + c] = bf16(src[r * cols + c])
+__global__ void pack_linear_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols,
+                                   long long ldd) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(rows) * cols) return;
+  const int r = static_cast<int>(idx / cols), c = static_cast<int>(idx % cols);
+  dst[r * ldd + c] = __float2bfloat16(src[idx]);
+}
+// Conv2d weight [Cout][Cin][3][3] -> [Cout][(kh*3+kw)][Cin_pad]
+__global__ void pack_conv3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cout, int Cin,
+                                  int Cin_pad) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(Cout) * Cin * 9) return;
+  const int tap = static_cast<int>(idx % 9);
+  const int ci = static_cast<int>((idx / 9) % Cin);
+  const int co = static_cast<int>(idx / (9LL * Cin));
+  dst[(static_cast<long long>(co) * 9 + tap) * Cin_pad + ci] = __float2bfloat16(src[idx]);
+}
+// ConvTranspose2d weight [Cin][Cout][k][k] -> [(kh*k+kw)*Cout_pad + co][Cin_pad]
+__global__ void pack_convT_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cin, int Cout,
+                                  int k, int Cin_pad, int Cout_pad) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(Cin) * Cout * k * k) return;
+  const int kk = static_cast<int>(idx % (k * k));
+  const int co = static_cast<int>((idx / (k * k)) % Cout);
+  const int ci = static_cast<int>(idx / (static_cast<long long>(k) * k * Cout));
+  dst[(static_cast<long long>(kk) * Cout_pad + co) * Cin_pad + ci] = __float2bfloat16(src[idx]);
+}
+// [rows][cols] fp32 -> [cols][rows] fp32
+__global__ void transpose_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int r = idx / cols, c = idx % cols;
+  dst[c * rows + r] = src[idx];
+}
+// decoder positions: [2B][N+1][2] int32 from two int64 [B][N][2] arrays, pose token at (-1,-1)
+__global__ void build_dec_pos_kernel(const long long* __restrict__ p1, const long long* __restrict__ p2, int B, int N,
+                                     int* __restrict__ out) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = 2LL * B * (N + 1);
+  if (idx >= total) return;
+  const int t = static_cast<int>(idx % (N + 1));
+  const int s = static_cast<int>(idx / (N + 1));
+  int y = -1, x = -1;
+  if (t > 0) {
+    const long long* p = (s < B) ? p1 + (static_cast<long long>(s) * N + (t - 1)) * 2
+                                 : p2 + (static_cast<long long>(s - B) * N + (t - 1)) * 2;
+    y = static_cast<int>(p[0]);
+    x = static_cast<int>(p[1]);
+  }
+  out[2 * idx] = y;
+  out[2 * idx + 1] = x;
+}
+__global__ void pos_to_int64_kernel(const int* __restrict__ in, long long n, long long* __restrict__ out) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx < n) out[idx] = in[idx];
+}
+// LayerNorm with fp32 output (all rows) -- only used by the per-layer-output compatibility path.
+__global__ void __launch_bounds__(256)
+layernorm_f32_kernel(const float* __restrict__ x, int rows, int C, float eps, const float* __restrict__ g,
+                     const float* __restrict__ b, float* __restrict__ out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + static_cast<long long>(row) * C;
+  float sum = 0.f;
+  for (int c = lane; c < C; c += 32) sum += xr[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = xr[c] - mean;
+    sq += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / C + eps);
+  float* orow = out + static_cast<long long>(row) * C;
+  for (int c = lane; c < C; c += 32) orow[c] = (xr[c] - mean) * rstd * g[c] + b[c];
+}
+
+// ---------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------
+struct Lin {
+  bf16* w = nullptr;  // [N][K]
+  float* b = nullptr; // [N] or null
+  int N = 0, K = 0;
+};
+struct LNp {
+  float *g = nullptr, *b = nullptr;
+};
+struct EncBlock {
+  LNp n1, n2;
+  Lin qkv, proj, fc1, fc2;
+};
+struct DecBlock {
+  LNp n1, n2, n3, ny;
+  Lin qkv, proj, cq, ckv, cproj, fc1, fc2;
+};
+struct Rcu {
+  Lin c1, c2;  // 3x3 256 -> 256
+};
+struct Refine {
+  Rcu r1, r2;
+  Lin out;  // 1x1
+};
+
+enum PackKind { PK_F32, PK_LINEAR, PK_CONV3, PK_CONVT, PK_TRANSPOSE_F32, PK_IGNORE };
+struct Slot {
+  PackKind kind;
+  std::vector<int64_t> shape;  // expected source shape
+  void* dst = nullptr;
+  long long ldd = 0;            // PK_LINEAR: destination row stride
+  int cin_pad = 0, cout_pad = 0, k = 0;
+  bool loaded = false;
+};
+
+struct Workspace {
+  char* base = nullptr;
+  size_t bytes = 0;
+  size_t off = 0;
+  int nimg = 0, h = 0, w = 0;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+}  // namespace sta
+
+using namespace sta;
+
+struct StaModel {
+  // ---- weights ----
+  char* arena = nullptr;
+  size_t arena_bytes = 0, arena_off = 0;
+  std::unordered_map<std::string, Slot> slots;
+  int missing = 0;
+
+  float* pose_tok = nullptr;
+  Lin patch, dec_embed;
+  EncBlock enc[24];
+  DecBlock dec[12];
+  LNp dec_norm;
+  // DPT
+  Lin act0, act0T, act1, act1T, act2, act3, act3c;
+  Lin rn[4];
+  Refine ref[4];  // ref[0] = refinenet1 ... ref[3] = refinenet4
+  Lin head0, head2;
+  float *head4_w = nullptr, *head4_b = nullptr;
+  PoseHeadWeights pose = {};
+
+  // ---- workspace ----
+  Workspace ws;
+  float* stage = nullptr;  // staging for host->device weight uploads
+  size_t stage_bytes = 0;
+  char* io = nullptr;      // device staging for sta_forward_pairs_host
+  size_t io_bytes = 0;
+  int64_t launches = 0;
+  int max_pairs_per_chunk = 16;
+
+  template <typename T>
+  T* alloc(size_t n) {
+    arena_off = (arena_off + 255) & ~static_cast<size_t>(255);
+    T* p = reinterpret_cast<T*>(arena + arena_off);
+    arena_off += n * sizeof(T);
+    return p;
+  }
+};
+
+namespace {
+
+constexpr float kLnEps = 1e-6f;
+constexpr int kEncDim = 1024, kDecDim = 768, kEncHeads = 16, kDecHeads = 12;
+
+void add_slot(StaModel* m, const std::string& name, PackKind kind, std::vector<int64_t> shape, void* dst,
+              long long ldd = 0, int cin_pad = 0, int cout_pad = 0, int k = 0) {
+  Slot s;
+  s.kind = kind;
+  s.shape = std::move(shape);
+  s.dst = dst;
+  s.ldd = ldd;
+  s.cin_pad = cin_pad;
+  s.cout_pad = cout_pad;
+  s.k = k;
+  m->slots[name] = s;
+  if (kind != PK_IGNORE) m->missing++;
+}
+
+// linear [N][K] (+bias) registered under prefix.weight / prefix.bias; optional zero padding of N
+void reg_linear(StaModel* m, const std::string& prefix, Lin* L, int N, int K, bool bias = true, int N_pad = 0,
+                std::vector<int64_t> wshape = {}) {
+  const int Np = N_pad > 0 ? N_pad : N;
+  L->N = Np;
+  L->K = K;
+  L->w = m->alloc<bf16>(static_cast<size_t>(Np) * K);
+  if (wshape.empty()) wshape = {N, K};
+  add_slot(m, prefix + ".weight", PK_LINEAR, wshape, L->w, K);
+  if (bias) {
+    L->b = m->alloc<float>(Np);
+    add_slot(m, prefix + ".bias", PK_F32, {N}, L->b);
+  }
+}
+void reg_ln(StaModel* m, const std::string& prefix, LNp* p, int C) {
+  p->g = m->alloc<float>(C);
+  p->b = m->alloc<float>(C);
+  add_slot(m, prefix + ".weight", PK_F32, {C}, p->g);
+  add_slot(m, prefix + ".bias", PK_F32, {C}, p->b);
+}
+void reg_conv3(StaModel* m, const std::string& prefix, Lin* L, int Cout, int Cin, bool bias, int Cin_pad = 0) {
+  const int Cp = Cin_pad > 0 ? Cin_pad : Cin;
+  L->N = Cout;
+  L->K = 9 * Cp;
+  L->w = m->alloc<bf16>(static_cast<size_t>(Cout) * 9 * Cp);
+  add_slot(m, prefix + ".weight", PK_CONV3, {Cout, Cin, 3, 3}, L->w, 0, Cp);
+  if (bias) {
+    L->b = m->alloc<float>(Cout);
+    add_slot(m, prefix + ".bias", PK_F32, {Cout}, L->b);
+  }
+}
+void reg_convT(StaModel* m, const std::string& prefix, Lin* L, int C, int k, int C_pad) {
+  L->N = k * k * C_pad;
+  L->K = C_pad;
+  L->w = m->alloc<bf16>(static_cast<size_t>(L->N) * L->K);
+  add_slot(m, prefix + ".weight", PK_CONVT, {C, C, k, k}, L->w, 0, C_pad, C_pad, k);
+  L->b = m->alloc<float>(C_pad);  // indexed by output channel
+  add_slot(m, prefix + ".bias", PK_F32, {C}, L->b);
+}
+void reg_f32(StaModel* m, const std::string& name, float** dst, std::vector<int64_t> shape) {
+  size_t n = 1;
+  for (auto d : shape) n *= static_cast<size_t>(d);
+  *dst = m->alloc<float>(n);
+  add_slot(m, name, PK_F32, shape, *dst);
+}
+
+int build_registry(StaModel* m) {
+  reg_f32(m, "init_pose_token", &m->pose_tok, {1, 1, kDecDim});
+  reg_linear(m, "patch_embed.proj", &m->patch, kEncDim, 768, true, 0, {kEncDim, 3, 16, 16});
+  for (int i = 0; i < 24; ++i) {
+    const std::string p = "enc_blocks." + std::to_string(i) + ".";
+    EncBlock& b = m->enc[i];
+    reg_ln(m, p + "norm1", &b.n1, kEncDim);
+    reg_linear(m, p + "attn.qkv", &b.qkv, 3 * kEncDim, kEncDim);
+    reg_linear(m, p + "attn.proj", &b.proj, kEncDim, kEncDim);
+    reg_ln(m, p + "norm2", &b.n2, kEncDim);
+    reg_linear(m, p + "mlp.fc1", &b.fc1, 4 * kEncDim, kEncDim);
+    reg_linear(m, p + "mlp.fc2", &b.fc2, kEncDim, 4 * kEncDim);
+  }
+  add_slot(m, "enc_norm.weight", PK_IGNORE, {kEncDim}, nullptr);  // never applied (normalize=False everywhere)
+  add_slot(m, "enc_norm.bias", PK_IGNORE, {kEncDim}, nullptr);
+  reg_linear(m, "decoder_embed", &m->dec_embed, kDecDim, kEncDim);
+  for (int i = 0; i < 12; ++i) {
+    const std::string p = "dec_block." + std::to_string(i) + ".";
+    DecBlock& b = m->dec[i];
+    reg_ln(m, p + "norm1", &b.n1, kDecDim);
+    reg_linear(m, p + "attn.qkv", &b.qkv, 3 * kDecDim, kDecDim);
+    reg_linear(m, p + "attn.proj", &b.proj, kDecDim, kDecDim);
+    reg_linear(m, p + "cross_attn.projq", &b.cq, kDecDim, kDecDim);
+    // projk and projv are fused into one [1536][768] matrix (both act on norm_y(y))
+    b.ckv.N = 2 * kDecDim;
+    b.ckv.K = kDecDim;
+    b.ckv.w = m->alloc<bf16>(static_cast<size_t>(2) * kDecDim * kDecDim);
+    b.ckv.b = m->alloc<float>(2 * kDecDim);
+    add_slot(m, p + "cross_attn.projk.weight", PK_LINEAR, {kDecDim, kDecDim}, b.ckv.w, kDecDim);
+    add_slot(m, p + "cross_attn.projk.bias", PK_F32, {kDecDim}, b.ckv.b);
+    add_slot(m, p + "cross_attn.projv.weight", PK_LINEAR, {kDecDim, kDecDim},
+             b.ckv.w + static_cast<size_t>(kDecDim) * kDecDim, kDecDim);
+    add_slot(m, p + "cross_attn.projv.bias", PK_F32, {kDecDim}, b.ckv.b + kDecDim);
+    reg_linear(m, p + "cross_attn.proj", &b.cproj, kDecDim, kDecDim);
+    reg_ln(m, p + "norm2", &b.n2, kDecDim);
+    reg_ln(m, p + "norm3", &b.n3, kDecDim);
+    reg_linear(m, p + "mlp.fc1", &b.fc1, 4 * kDecDim, kDecDim);
+    reg_linear(m, p + "mlp.fc2", &b.fc2, kDecDim, 4 * kDecDim);
+    reg_ln(m, p + "norm_y", &b.ny, kDecDim);
+  }
+  reg_ln(m, "dec_norm", &m->dec_norm, kDecDim);
+
+  const std::string d = "downstream_head_pts.dpt.";
+  const int rn_cin[4] = {96, 192, 384, 768};
+  const int rn_cin_pad[4] = {128, 192, 384, 768};
+  for (int i = 0; i < 4; ++i) {
+    reg_conv3(m, d + "scratch.layer_rn." + std::to_string(i), &m->rn[i], 256, rn_cin[i], false, rn_cin_pad[i]);
+    // the same Parameter is also registered as scratch.layer{i+1}_rn (dpt_block.py:33-75)
+    add_slot(m, d + "scratch.layer" + std::to_string(i + 1) + "_rn.weight", PK_IGNORE, {256, rn_cin[i], 3, 3}, nullptr);
+  }
+  for (int i = 0; i < 4; ++i) {
+    const std::string p = d + "scratch.refinenet" + std::to_string(i + 1) + ".";
+    Refine& r = m->ref[i];
+    reg_linear(m, p + "out_conv", &r.out, 256, 256, true, 0, {256, 256, 1, 1});
+    if (i == 3) {  // refinenet4 is called with one input: resConfUnit1 is never used (dpt_block.py:189-197)
+      for (const char* c : {"conv1", "conv2"}) {
+        add_slot(m, p + "resConfUnit1." + c + ".weight", PK_IGNORE, {256, 256, 3, 3}, nullptr);
+        add_slot(m, p + "resConfUnit1." + c + ".bias", PK_IGNORE, {256}, nullptr);
+      }
+    } else {
+      reg_conv3(m, p + "resConfUnit1.conv1", &r.r1.c1, 256, 256, true);
+      reg_conv3(m, p + "resConfUnit1.conv2", &r.r1.c2, 256, 256, true);
+    }
+    reg_conv3(m, p + "resConfUnit2.conv1", &r.r2.c1, 256, 256, true);
+    reg_conv3(m, p + "resConfUnit2.conv2", &r.r2.c2, 256, 256, true);
+  }
+  reg_conv3(m, d + "head.0", &m->head0, 128, 256, true);
+  reg_conv3(m, d + "head.2", &m->head2, 128, 128, true);
+  m->head4_w = m->alloc<float>(128 * 4);
+  add_slot(m, d + "head.4.weight", PK_TRANSPOSE_F32, {4, 128, 1, 1}, m->head4_w);
+  reg_f32(m, d + "head.4.bias", &m->head4_b, {4});
+  reg_linear(m, d + "act_postprocess.0.0", &m->act0, 96, kEncDim, true, 128, {96, kEncDim, 1, 1});
+  reg_convT(m, d + "act_postprocess.0.1", &m->act0T, 96, 4, 128);
+  reg_linear(m, d + "act_postprocess.1.0", &m->act1, 192, kDecDim, true, 0, {192, kDecDim, 1, 1});
+  reg_convT(m, d + "act_postprocess.1.1", &m->act1T, 192, 2, 192);
+  reg_linear(m, d + "act_postprocess.2.0", &m->act2, 384, kDecDim, true, 0, {384, kDecDim, 1, 1});
+  reg_linear(m, d + "act_postprocess.3.0", &m->act3, 768, kDecDim, true, 0, {768, kDecDim, 1, 1});
+  reg_conv3(m, d + "act_postprocess.3.1", &m->act3c, 768, 768, true);
+
+  float* tmp = nullptr;
+  auto regp = [&](const std::string& name, const float** dst, std::vector<int64_t> shape) {
+    reg_f32(m, name, &tmp, shape);
+    *dst = tmp;
+  };
+  m->pose.ln_g = m->dec_norm.g;
+  m->pose.ln_b = m->dec_norm.b;
+  regp("head_pose_s.mlp.0.weight", &m->pose.w0, {512, kDecDim});
+  regp("head_pose_s.mlp.0.bias", &m->pose.b0, {512});
+  regp("head_pose_s.mlp.2.weight", &m->pose.w1, {512, 512});
+  regp("head_pose_s.mlp.2.bias", &m->pose.b1, {512});
+  regp("head_pose_s.mlp.4.weight", &m->pose.w2, {512, 512});
+  regp("head_pose_s.mlp.4.bias", &m->pose.b2, {512});
+  regp("head_pose_s.fc_t.weight", &m->pose.wt, {3, 512});
+  regp("head_pose_s.fc_t.bias", &m->pose.bt, {3});
+  regp("head_pose_s.fc_conf.0.weight", &m->pose.wc, {1, 512});
+  regp("head_pose_s.fc_conf.0.bias", &m->pose.bc, {1});
+  regp("head_pose_s.fc_rot.weight", &m->pose.wr, {9, 512});
+  regp("head_pose_s.fc_rot.bias", &m->pose.br, {9});
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// launch helpers (all increment the model's launch counter)
+// ---------------------------------------------------------------------------
+struct Ctx {
+  StaModel* m;
+  cudaStream_t st;
+};
+
+int gemm(const Ctx& c, int amode, int epi, const bf16* A, long long lda, const Lin& L, GemmParams p) {
+  GemmLaunch g;
+  g.amode = amode;
+  g.epi = epi;
+  g.A = A;
+  g.lda = lda;
+  g.Wt = L.w;
+  g.ldw = L.K;
+  p.N = L.N;
+  p.K = L.K;
+  if (!p.bias) p.bias = L.b;
+  g.p = p;
+  c.m->launches++;
+  return launch_gemm(g, c.st);
+}
+// plain linear on rows
+int linear(const Ctx& c, int epi, const bf16* A, int M, const Lin& L, void* out, const void* resid = nullptr,
+           const int* pos = nullptr, int rope_cols = 0, int rowmap_n = 0) {
+  GemmParams p = {};
+  p.M = M;
+  p.out = out;
+  p.ldo = L.N;
+  p.resid = resid;
+  p.rowmap_n = rowmap_n;
+  if (epi == EPI_ROPE) {
+    p.pos = pos;
+    p.rope_cols = rope_cols;
+    p.rope_tab = rope_table(&p.rope_max_pos);
+    if (!p.rope_tab) {
+      set_last_error("failed to build the RoPE table");
+      return 1;
+    }
+  }
+  return gemm(c, A_LINEAR, epi, A, L.K, L, p);
+}
+int conv3(const Ctx& c, const bf16* in, int nimg, int H, int W, int Cin, const Lin& L, bf16* out, bf16* out_relu,
+          const bf16* resid, const bf16* resid2, int relu_main) {
+  GemmParams p = {};
+  p.nimg = nimg;
+  p.H = H;
+  p.W = W;
+  p.Cin = Cin;
+  p.out = out;
+  p.out2 = out_relu;
+  p.ldo = L.N;
+  p.resid = resid;
+  p.resid2 = resid2;
+  p.relu_main = relu_main;
+  return gemm(c, A_CONV3, EPI_BF16, in, 0, L, p);
+}
+int ln(const Ctx& c, const float* x, int rows, int C, const LNp& a, bf16* out1, const LNp* b2 = nullptr,
+       bf16* out2 = nullptr, int drop_first_of = 0) {
+  c.m->launches++;
+  return launch_layernorm(x, rows, C, kLnEps, a.g, a.b, out1, b2 ? b2->g : nullptr, b2 ? b2->b : nullptr, out2,
+                          drop_first_of, c.st);
+}
+int attn(const Ctx& c, const bf16* q, long long ldq, int qc, const bf16* k, long long ldk, int kc, const bf16* v,
+         long long ldv, int vc, bf16* out, long long ldo, int batch, int heads, int nq, int nk, int shift) {
+  AttnLaunch a;
+  a.q = q; a.ldq = ldq; a.q_col0 = qc;
+  a.k = k; a.ldk = ldk; a.k_col0 = kc;
+  a.v = v; a.ldv = ldv; a.v_col0 = vc;
+  a.out = out; a.ldo = ldo;
+  a.batch = batch; a.heads = heads; a.nq = nq; a.nk = nk;
+  a.kv_batch_shift = shift;
+  a.scale = 0.125f;  // head_dim ** -0.5, sta_blocks.py:86
+  c.m->launches++;
+  return launch_attention(a, c.st);
+}
+
+#define RUN(expr)            \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc) return _rc;     \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------
+struct EncBufs {
+  bf16 *patches, *lnb, *qkv, *att, *hid;
+  int* pos;
+};
+struct DecBufs {
+  float* xd;
+  bf16 *enc_bf16, *ln1, *lny, *qkv, *att, *qc, *kvc, *hid, *hook[3];
+  int* pos;
+};
+struct DptBufs {
+  bf16 *a0, *l1, *a1, *l2, *l3, *a3, *col4, *l4;
+  bf16 *r_raw[4], *r_relu[4];
+  bf16 *t1, *t2, *s_raw, *s_relu, *o, *up, *path;  // sized for the largest level
+  bf16 *hc1, *hup;
+};
+
+size_t ws_need(int nimg, int h, int w) {
+  const size_t N = static_cast<size_t>(h) * w, T = nimg * N, Td = nimg * (N + 1);
+  size_t b = 0;
+  auto add = [&](size_t n) { b += ((n + 255) / 256) * 256 + 256; };
+  // encoder
+  add(T * 768 * 2); add(T * 1024 * 2); add(T * 3072 * 2); add(T * 1024 * 2); add(T * 4096 * 2); add(T * 8);
+  add(T * 1024 * 4);  // x (fp32 residual stream)
+  // decoder
+  add(Td * 768 * 4); add(T * 1024 * 2); add(Td * 768 * 2 * 2); add(Td * 2304 * 2); add(Td * 768 * 2 * 2);
+  add(Td * 1536 * 2); add(Td * 3072 * 2); add(T * 768 * 2 * 3); add(Td * 8);
+  // dpt
+  const size_t h4 = (h + 1) / 2, w4 = (w + 1) / 2;
+  const size_t P1 = 16 * N, P2 = 4 * N, P3 = N, P4 = h4 * w4;
+  add(T * 128 * 2); add(nimg * P1 * 128 * 2); add(T * 192 * 2); add(nimg * P2 * 192 * 2); add(T * 384 * 2);
+  add(T * 768 * 2); add(nimg * P4 * 6912 * 2); add(nimg * P4 * 768 * 2);
+  const size_t P[4] = {P1, P2, P3, P4};
+  for (int i = 0; i < 4; ++i) { add(nimg * P[i] * 256 * 2); add(nimg * P[i] * 256 * 2); }
+  for (int i = 0; i < 5; ++i) add(nimg * P1 * 256 * 2);       // t1, t2, s_raw, s_relu, o
+  add(nimg * 64 * N * 256 * 2); add(nimg * 64 * N * 256 * 2);  // up, path (up to 8h x 8w)
+  add(nimg * 64 * N * 128 * 2); add(nimg * 256 * N * 128 * 2); // hc1, hup (full res)
+  return b + (1 << 20);
+}
+
+int ensure_ws(StaModel* m, int nimg, int h, int w) {
+  const size_t need = ws_need(nimg, h, w);
+  if (m->ws.bytes < need) {
+    STA_CHECK_CUDA(cudaDeviceSynchronize());
+    if (m->ws.base) STA_CHECK_CUDA(cudaFree(m->ws.base));
+    m->ws.base = nullptr;
+    m->ws.bytes = 0;
+    STA_CHECK_CUDA(cudaMalloc(&m->ws.base, need));
+    m->ws.bytes = need;
+  }
+  m->ws.off = 0;
+  m->ws.nimg = nimg;
+  m->ws.h = h;
+  m->ws.w = w;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// encoder over nimg images whose patches (e.patches) and positions (e.pos) are prepared.
+// x: fp32 residual stream [nimg*N][1024], provided by the caller (user buffer or workspace);
+// on return it holds the un-normalised encoder features (normalize=False, sta_model.py:172).
+// ---------------------------------------------------------------------------
+int run_encoder(const Ctx& c, int nimg, int N, float* x, EncBufs& e) {
+  StaModel* m = c.m;
+  const int T = nimg * N;
+  RUN(linear(c, EPI_F32, e.patches, T, m->patch, x));
+  for (int l = 0; l < 24; ++l) {
+    const EncBlock& b = m->enc[l];
+    RUN(ln(c, x, T, kEncDim, b.n1, e.lnb));
+    RUN(linear(c, EPI_ROPE, e.lnb, T, b.qkv, e.qkv, nullptr, e.pos, 2 * kEncDim));
+    RUN(attn(c, e.qkv, 3 * kEncDim, 0, e.qkv, 3 * kEncDim, kEncDim, e.qkv, 3 * kEncDim, 2 * kEncDim, e.att, kEncDim,
+             nimg, kEncHeads, N, N, 0));
+    RUN(linear(c, EPI_F32, e.att, T, b.proj, x, x));
+    RUN(ln(c, x, T, kEncDim, b.n2, e.lnb));
+    RUN(linear(c, EPI_GELU, e.lnb, T, b.fc1, e.hid));
+    RUN(linear(c, EPI_F32, e.hid, T, b.fc2, x, x));
+  }
+  return 0;
+}
+
+EncBufs take_enc(Workspace& ws, int nimg, int N) {
+  const size_t T = static_cast<size_t>(nimg) * N;
+  EncBufs e;
+  e.patches = ws.take<bf16>(T * 768);
+  e.lnb = ws.take<bf16>(T * 1024);
+  e.qkv = ws.take<bf16>(T * 3072);
+  e.att = ws.take<bf16>(T * 1024);
+  e.hid = ws.take<bf16>(T * 4096);
+  e.pos = ws.take<int>(T * 2);
+  return e;
+}
+DecBufs take_dec(Workspace& ws, int S, int N) {
+  const size_t T = static_cast<size_t>(S) * N, Td = static_cast<size_t>(S) * (N + 1);
+  DecBufs d;
+  d.xd = ws.take<float>(Td * 768);
+  d.enc_bf16 = ws.take<bf16>(T * 1024);
+  d.ln1 = ws.take<bf16>(Td * 768);
+  d.lny = ws.take<bf16>(Td * 768);
+  d.qkv = ws.take<bf16>(Td * 2304);
+  d.att = ws.take<bf16>(Td * 768);
+  d.qc = ws.take<bf16>(Td * 768);
+  d.kvc = ws.take<bf16>(Td * 1536);
+  d.hid = ws.take<bf16>(Td * 3072);
+  for (int i = 0; i < 3; ++i) d.hook[i] = ws.take<bf16>(T * 768);
+  d.pos = ws.take<int>(Td * 2);
+  return d;
+}
+
+// ---------------------------------------------------------------------------
+// symmetric decoder over S = 2B samples (samples [0,B) = view 1, [B,2B) = view 2).
+// d.enc_bf16 (bf16 encoder features of all S samples) and d.pos must be filled.
+// outs: optional 2 x 13 fp32 per-layer outputs (compat path), may be null.
+// ---------------------------------------------------------------------------
+int run_decoder(const Ctx& c, int B, int N, DecBufs& d, float* const* out1, float* const* out2) {
+  StaModel* m = c.m;
+  const int S = 2 * B, M = N + 1, T = S * N, Td = S * M;
+  const long long half = static_cast<long long>(B) * M * kDecDim;
+  auto emit = [&](int idx) -> int {
+    if (out1 && out1[idx]) { m->launches++; RUN(launch_copy_f32(d.xd, out1[idx], half, c.st)); }
+    if (out2 && out2[idx]) { m->launches++; RUN(launch_copy_f32(d.xd + half, out2[idx], half, c.st)); }
+    return 0;
+  };
+  RUN(linear(c, EPI_F32, d.enc_bf16, T, m->dec_embed, d.xd, nullptr, nullptr, 0, N));
+  m->launches++;
+  RUN(launch_fill_pose_token(d.xd, m->pose_tok, S, M, kDecDim, c.st));
+  RUN(emit(0));
+  for (int l = 0; l < 12; ++l) {
+    const DecBlock& b = m->dec[l];
+    // self-attention on norm1(x); norm_y(x) is what the partner view cross-attends to
+    RUN(ln(c, d.xd, Td, kDecDim, b.n1, d.ln1, &b.ny, d.lny));
+    RUN(linear(c, EPI_ROPE, d.ln1, Td, b.qkv, d.qkv, nullptr, d.pos, 2 * kDecDim));
+    RUN(attn(c, d.qkv, 3 * kDecDim, 0, d.qkv, 3 * kDecDim, kDecDim, d.qkv, 3 * kDecDim, 2 * kDecDim, d.att, kDecDim, S,
+             kDecHeads, M, M, 0));
+    RUN(linear(c, EPI_F32, d.att, Td, b.proj, d.xd, d.xd));
+    // cross-attention: q from norm2(x), k/v from norm_y(partner input) -- kv sample = (s + B) % 2B
+    RUN(linear(c, EPI_ROPE, d.lny, Td, b.ckv, d.kvc, nullptr, d.pos, kDecDim));
+    RUN(ln(c, d.xd, Td, kDecDim, b.n2, d.ln1));
+    RUN(linear(c, EPI_ROPE, d.ln1, Td, b.cq, d.qc, nullptr, d.pos, kDecDim));
+    RUN(attn(c, d.qc, kDecDim, 0, d.kvc, 2 * kDecDim, 0, d.kvc, 2 * kDecDim, kDecDim, d.att, kDecDim, S, kDecHeads, M, M,
+             B));
+    RUN(linear(c, EPI_F32, d.att, Td, b.cproj, d.xd, d.xd));
+    // MLP
+    RUN(ln(c, d.xd, Td, kDecDim, b.n3, d.ln1));
+    RUN(linear(c, EPI_GELU, d.ln1, Td, b.fc1, d.hid));
+    RUN(linear(c, EPI_F32, d.hid, Td, b.fc2, d.xd, d.xd));
+    if (l + 1 == 6 || l + 1 == 9) {  // DPT hooks [0, 7, 10, 13] -> decoder outputs 6, 9, 12 (dpt_head.py:112)
+      m->launches++;
+      RUN(launch_cast_f32_bf16(d.xd, d.hook[l + 1 == 6 ? 0 : 1], Td, kDecDim, M, c.st));
+    }
+    if (l + 1 < 12) RUN(emit(l + 1));
+  }
+  // dec_norm on the last output; bf16 copy without the pose token feeds the DPT head
+  RUN(ln(c, d.xd, Td, kDecDim, m->dec_norm, d.hook[2], nullptr, nullptr, M));
+  if ((out1 && out1[12]) || (out2 && out2[12])) {
+    // compat path: fp32 LayerNorm-ed last layer
+    const int rows_half = B * M;
+    if (out1 && out1[12]) {
+      m->launches++;
+      layernorm_f32_kernel<<<(rows_half + 7) / 8, 256, 0, c.st>>>(d.xd, rows_half, kDecDim, kLnEps, m->dec_norm.g,
+                                                                  m->dec_norm.b, out1[12]);
+    }
+    if (out2 && out2[12]) {
+      m->launches++;
+      layernorm_f32_kernel<<<(rows_half + 7) / 8, 256, 0, c.st>>>(d.xd + half, rows_half, kDecDim, kLnEps,
+                                                                  m->dec_norm.g, m->dec_norm.b, out2[12]);
+    }
+    STA_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// DPT head over nimg images.  hooks: bf16 token matrices [nimg*N][1024 | 768 | 768 | 768].
+// ---------------------------------------------------------------------------
+int run_dpt(const Ctx& c, Workspace& ws, int nimg, int h, int w, const bf16* hook0, const bf16* hook1,
+            const bf16* hook2, const bf16* hook3, float* pts3d, float* conf) {
+  StaModel* m = c.m;
+  const int N = h * w, T = nimg * N;
+  const int h4 = (h + 1) / 2, w4 = (w + 1) / 2;
+  const int LH[4] = {4 * h, 2 * h, h, h4}, LW[4] = {4 * w, 2 * w, w, w4};
+  DptBufs b;
+  b.a0 = ws.take<bf16>(static_cast<size_t>(T) * 128);
+  b.l1 = ws.take<bf16>(static_cast<size_t>(nimg) * 16 * N * 128);
+  b.a1 = ws.take<bf16>(static_cast<size_t>(T) * 192);
+  b.l2 = ws.take<bf16>(static_cast<size_t>(nimg) * 4 * N * 192);
+  b.l3 = ws.take<bf16>(static_cast<size_t>(T) * 384);
+  b.a3 = ws.take<bf16>(static_cast<size_t>(T) * 768);
+  b.col4 = ws.take<bf16>(static_cast<size_t>(nimg) * h4 * w4 * 6912);
+  b.l4 = ws.take<bf16>(static_cast<size_t>(nimg) * h4 * w4 * 768);
+  for (int i = 0; i < 4; ++i) {
+    b.r_raw[i] = ws.take<bf16>(static_cast<size_t>(nimg) * LH[i] * LW[i] * 256);
+    b.r_relu[i] = ws.take<bf16>(static_cast<size_t>(nimg) * LH[i] * LW[i] * 256);
+  }
+  const size_t big = static_cast<size_t>(nimg) * 16 * N * 256;
+  b.t1 = ws.take<bf16>(big);
+  b.t2 = ws.take<bf16>(big);
+  b.s_raw = ws.take<bf16>(big);
+  b.s_relu = ws.take<bf16>(big);
+  b.o = ws.take<bf16>(big);
+  b.up = ws.take<bf16>(static_cast<size_t>(nimg) * 64 * N * 256);
+  b.path = ws.take<bf16>(static_cast<size_t>(nimg) * 64 * N * 256);
+  b.hc1 = ws.take<bf16>(static_cast<size_t>(nimg) * 64 * N * 128);
+  b.hup = ws.take<bf16>(static_cast<size_t>(nimg) * 256 * N * 128);
+
+  // ---- act_postprocess (dpt_block.py:356-410) ----
+  RUN(linear(c, EPI_BF16, hook0, T, m->act0, b.a0));
+  {
+    GemmParams p = {};
+    p.M = T; p.out = b.l1; p.ps_k = 4; p.ps_cout = 128; p.ps_h = h; p.ps_w = w;
+    RUN(gemm(c, A_LINEAR, EPI_PIXSHUF, b.a0, 128, m->act0T, p));
+  }
+  RUN(linear(c, EPI_BF16, hook1, T, m->act1, b.a1));
+  {
+    GemmParams p = {};
+    p.M = T; p.out = b.l2; p.ps_k = 2; p.ps_cout = 192; p.ps_h = h; p.ps_w = w;
+    RUN(gemm(c, A_LINEAR, EPI_PIXSHUF, b.a1, 192, m->act1T, p));
+  }
+  RUN(linear(c, EPI_BF16, hook2, T, m->act2, b.l3));
+  RUN(linear(c, EPI_BF16, hook3, T, m->act3, b.a3));
+  m->launches++;
+  RUN(launch_im2col_3x3_s2(b.a3, b.col4, nimg, h, w, 768, c.st));
+  RUN(linear(c, EPI_BF16, b.col4, nimg * h4 * w4, m->act3c, b.l4));
+  // ---- layer_rn: 3x3 conv to 256 channels, no bias (dpt_block.py:33-75); raw + relu copies ----
+  const bf16* lin[4] = {b.l1, b.l2, b.l3, b.l4};
+  const int lc[4] = {128, 192, 384, 768};
+  for (int i = 0; i < 4; ++i)
+    RUN(conv3(c, lin[i], nimg, LH[i], LW[i], lc[i], m->rn[i], b.r_raw[i], b.r_relu[i], nullptr, nullptr, 0));
+
+  // ---- refinenet4 .. refinenet1 (dpt_block.py:189-218, dpt_head.py:58-61) ----
+  const bf16* path = nullptr;  // output of the previous (coarser) fusion block at this level's resolution
+  for (int lvl = 3; lvl >= 0; --lvl) {
+    const Refine& r = m->ref[lvl];
+    const int Hh = LH[lvl], Ww = LW[lvl];
+    const bf16* s_raw;
+    const bf16* s_relu;
+    if (lvl == 3) {
+      s_raw = b.r_raw[3];
+      s_relu = b.r_relu[3];
+    } else {
+      // res = RCU1(layer); s = path + res
+      RUN(conv3(c, b.r_relu[lvl], nimg, Hh, Ww, 256, r.r1.c1, b.t1, nullptr, nullptr, nullptr, 1));
+      RUN(conv3(c, b.t1, nimg, Hh, Ww, 256, r.r1.c2, b.s_raw, b.s_relu, b.r_raw[lvl], path, 0));
+      s_raw = b.s_raw;
+      s_relu = b.s_relu;
+    }
+    // out = RCU2(s)
+    RUN(conv3(c, s_relu, nimg, Hh, Ww, 256, r.r2.c1, b.t2, nullptr, nullptr, nullptr, 1));
+    RUN(conv3(c, b.t2, nimg, Hh, Ww, 256, r.r2.c2, b.o, nullptr, s_raw, nullptr, 0));
+    // bilinear x2 (align_corners=True), cropped to the next level's size for refinenet4 (dpt_head.py:58)
+    int OH = 2 * Hh, OW = 2 * Ww;
+    if (lvl == 3) { OH = LH[2]; OW = LW[2]; }
+    m->launches++;
+    RUN(launch_upsample2x(b.o, b.up, nimg, Hh, Ww, 256, OH, OW, c.st));
+    RUN(linear(c, EPI_BF16, b.up, nimg * OH * OW, r.out, b.path));
+    path = b.path;
+  }
+  // ---- head (dpt_block.py:318-324) + postprocess (postprocess.py:10-62) ----
+  const int H8 = 8 * h, W8 = 8 * w;
+  RUN(conv3(c, b.path, nimg, H8, W8, 256, m->head0, b.hc1, nullptr, nullptr, nullptr, 0));
+  m->launches++;
+  RUN(launch_upsample2x(b.hc1, b.hup, nimg, H8, W8, 128, 2 * H8, 2 * W8, c.st));
+  {
+    GemmParams p = {};
+    p.nimg = nimg; p.H = 2 * H8; p.W = 2 * W8; p.Cin = 128;
+    p.head_w = m->head4_w; p.head_b = m->head4_b; p.pts3d = pts3d; p.conf = conf;
+    RUN(gemm(c, A_CONV3, EPI_HEAD, b.hup, 0, m->head2, p));
+  }
+  return 0;
+}
+
+int check_ready(StaModel* m) {
+  if (!m) {
+    set_last_error("null model handle");
+    return 2;
+  }
+  if (m->missing != 0) {
+    char buf[128];
+    snprintf(buf, sizeof(buf), "model is missing %d state-dict tensors", m->missing);
+    set_last_error(buf);
+    return 2;
+  }
+  return 0;
+}
+
+int forward_chunk(const Ctx& c, const void* img1, const void* img2, int img_is_bf16, int B, int H, int W,
+                  float* pts3d, float* conf, float* pose, float* pose_conf, int B_total) {
+  StaModel* m = c.m;
+  const int h = H / 16, w = W / 16, N = h * w, S = 2 * B, M = N + 1;
+  RUN(ensure_ws(m, S, h, w));
+  Workspace& ws = m->ws;
+  float* x = ws.take<float>(static_cast<size_t>(S) * N * kEncDim);
+  EncBufs e = take_enc(ws, S, N);
+  DecBufs d = take_dec(ws, S, N);
+  // encode both views as one batch of 2B images: [view 1 batch ; view 2 batch]
+  m->launches += 3;
+  RUN(launch_patch_im2col(img1, img_is_bf16, B, H, W, e.patches, c.st));
+  RUN(launch_patch_im2col(img2, img_is_bf16, B, H, W, e.patches + static_cast<size_t>(B) * N * 768, c.st));
+  RUN(launch_make_positions(e.pos, S, h, w, 0, c.st));
+  RUN(run_encoder(c, S, N, x, e));
+  m->launches += 2;
+  RUN(launch_cast_f32_bf16(x, d.enc_bf16, static_cast<long long>(S) * N, kEncDim, 0, c.st));
+  RUN(launch_make_positions(d.pos, S, h, w, 1, c.st));
+  RUN(run_decoder(c, B, N, d, nullptr, nullptr));
+  // pose heads on the (dec_norm-ed) pose tokens of both views
+  {
+    // outputs are laid out [2][B_total]: view 1 block then view 2 block
+    m->launches += 2;
+    RUN(launch_pose_head(d.xd, static_cast<long long>(M) * kDecDim, B, 1, kLnEps, m->pose, pose, pose_conf, c.st));
+    RUN(launch_pose_head(d.xd + static_cast<long long>(B) * M * kDecDim, static_cast<long long>(M) * kDecDim, B, 1,
+                         kLnEps, m->pose, pose + static_cast<long long>(B_total) * 16, pose_conf + B_total, c.st));
+  }
+  // DPT heads: view 1 images then view 2 images (outputs are [2][B_total] blocks)
+  const long long px = static_cast<long long>(H) * W;
+  for (int v = 0; v < 2; ++v) {
+    const size_t save = ws.off;
+    const size_t tok0 = static_cast<size_t>(v) * B * N;
+    RUN(run_dpt(c, ws, B, h, w, d.enc_bf16 + tok0 * 1024, d.hook[0] + tok0 * 768, d.hook[1] + tok0 * 768,
+                d.hook[2] + tok0 * 768, pts3d + static_cast<long long>(v) * B_total * px * 3,
+                conf + static_cast<long long>(v) * B_total * px));
+    ws.off = save;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+const char* sta_last_error(void) { return get_last_error(); }
+int sta_version(void) { return 1; }
+
+int sta_device_synchronize(void) {
+  STA_CHECK_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+int sta_create(StaModel** out) {
+  if (!out) {
+    set_last_error("sta_create: null output pointer");
+    return 2;
+  }
+  *out = nullptr;
+  int dev = 0;
+  STA_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  STA_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "sta_b200 needs a Blackwell sm_100 GPU (found %s, sm_%d%d); there is no fallback path",
+             prop.name, prop.major, prop.minor);
+    set_last_error(buf);
+    return 3;
+  }
+  StaModel* m = new StaModel();
+  m->arena_bytes = static_cast<size_t>(960) << 20;  // 438.5 M params: ~877 MB bf16 + fp32 vectors + padding
+  cudaError_t e = cudaMalloc(&m->arena, m->arena_bytes);
+  if (e != cudaSuccess) {
+    set_last_error(std::string("cudaMalloc(weight arena) failed: ") + cudaGetErrorString(e));
+    delete m;
+    return 1;
+  }
+  cudaMemset(m->arena, 0, m->arena_bytes);
+  build_registry(m);
+  if (m->arena_off > m->arena_bytes) {
+    set_last_error("internal: weight arena too small");
+    cudaFree(m->arena);
+    delete m;
+    return 1;
+  }
+  *out = m;
+  return 0;
+}
+
+void sta_destroy(StaModel* m) {
+  if (!m) return;
+  cudaDeviceSynchronize();
+  if (m->arena) cudaFree(m->arena);
+  if (m->ws.base) cudaFree(m->ws.base);
+  if (m->stage) cudaFree(m->stage);
+  if (m->io) cudaFree(m->io);
+  delete m;
+}
+
+int sta_missing_tensors(StaModel* m) { return m ? m->missing : -1; }
+int64_t sta_launch_count(StaModel* m) { return m ? m->launches : 0; }
+int64_t sta_device_bytes(StaModel* m) {
+  return m ? static_cast<int64_t>(m->arena_bytes + m->ws.bytes + m->stage_bytes + m->io_bytes) : 0;
+}
+int sta_weight_arena(StaModel* m, void** ptr, int64_t* bytes) {
+  if (!m || !ptr || !bytes) {
+    set_last_error("sta_weight_arena: null argument");
+    return 2;
+  }
+  *ptr = m->arena;
+  *bytes = static_cast<int64_t>((m->arena_off + 255) & ~static_cast<size_t>(255));
+  return 0;
+}
+int sta_mark_all_loaded(StaModel* m) {  // after the arena was filled by a broadcast from another rank
+  if (!m) return 2;
+  for (auto& kv : m->slots) kv.second.loaded = true;
+  m->missing = 0;
+  return 0;
+}
+
+int sta_load_tensor(StaModel* m, const char* name, const float* data, const int64_t* shape, int ndim,
+                    int data_on_device) {
+  if (!m || !name || !data) {
+    set_last_error("sta_load_tensor: null argument");
+    return 2;
+  }
+  auto it = m->slots.find(name);
+  if (it == m->slots.end()) {
+    set_last_error(std::string("unexpected key in state_dict: ") + name);
+    return 4;
+  }
+  Slot& s = it->second;
+  bool ok = static_cast<int>(s.shape.size()) == ndim;
+  size_t numel = 1;
+  for (int i = 0; ok && i < ndim; ++i) {
+    ok = (shape[i] == s.shape[i]);
+    numel *= static_cast<size_t>(shape[i]);
+  }
+  if (!ok) {
+    set_last_error(std::string("size mismatch for ") + name);
+    return 5;
+  }
+  if (s.kind == PK_IGNORE) return 0;
+  const float* src = data;
+  if (!data_on_device) {
+    if (m->stage_bytes < numel * sizeof(float)) {
+      STA_CHECK_CUDA(cudaDeviceSynchronize());
+      if (m->stage) STA_CHECK_CUDA(cudaFree(m->stage));
+      m->stage = nullptr;
+      m->stage_bytes = 0;
+      size_t want = numel * sizeof(float);
+      if (want < (static_cast<size_t>(32) << 20)) want = static_cast<size_t>(32) << 20;
+      STA_CHECK_CUDA(cudaMalloc(&m->stage, want));
+      m->stage_bytes = want;
+    }
+    STA_CHECK_CUDA(cudaMemcpy(m->stage, data, numel * sizeof(float), cudaMemcpyHostToDevice));
+    src = m->stage;
+  }
+  const int threads = 256;
+  const int blocks = static_cast<int>((numel + threads - 1) / threads);
+  switch (s.kind) {
+    case PK_F32:
+      STA_CHECK_CUDA(cudaMemcpy(s.dst, src, numel * sizeof(float), cudaMemcpyDeviceToDevice));
+      break;
+    case PK_LINEAR: {
+      const int rows = static_cast<int>(s.shape[0]);
+      const int cols = static_cast<int>(numel / rows);
+      pack_linear_kernel<<<blocks, threads>>>(src, static_cast<bf16*>(s.dst), rows, cols, s.ldd);
+      break;
+    }
+    case PK_CONV3:
+      pack_conv3_kernel<<<blocks, threads>>>(src, static_cast<bf16*>(s.dst), static_cast<int>(s.shape[0]),
+                                             static_cast<int>(s.shape[1]), s.cin_pad);
+      break;
+    case PK_CONVT:
+      pack_convT_kernel<<<blocks, threads>>>(src, static_cast<bf16*>(s.dst), static_cast<int>(s.shape[0]),
+                                             static_cast<int>(s.shape[1]), s.k, s.cin_pad, s.cout_pad);
+      break;
+    case PK_TRANSPOSE_F32:
+      transpose_f32_kernel<<<blocks, threads>>>(src, static_cast<float*>(s.dst), static_cast<int>(s.shape[0]),
+                                                static_cast<int>(numel / s.shape[0]));
+      break;
+    default:
+      break;
+  }
+  STA_CHECK_CUDA(cudaGetLastError());
+  STA_CHECK_CUDA(cudaDeviceSynchronize());  // the staging buffer is reused by the next call
+  if (!s.loaded) {
+    s.loaded = true;
+    m->missing--;
+  }
+  return 0;
+}
+
+int sta_encode(StaModel* m, const void* img_dev, int img_is_bf16, int B, int H, int W, float* feat_out_dev,
+               int64_t* pos_out_dev, void* stream) {
+  RUN(check_ready(m));
+  STA_REQUIRE(B > 0 && H % 16 == 0 && W % 16 == 0 && H > 0 && W > 0, "image size must be a positive multiple of 16");
+  STA_REQUIRE(H / 16 <= 1024 && W / 16 <= 1024, "token grid exceeds the RoPE table");
+  Ctx c{m, static_cast<cudaStream_t>(stream)};
+  const int h = H / 16, w = W / 16, N = h * w;
+  RUN(ensure_ws(m, B, h, w));
+  EncBufs e = take_enc(m->ws, B, N);
+  m->launches += 2;
+  RUN(launch_patch_im2col(img_dev, img_is_bf16, B, H, W, e.patches, c.st));
+  RUN(launch_make_positions(e.pos, B, h, w, 0, c.st));
+  RUN(run_encoder(c, B, N, feat_out_dev, e));
+  if (pos_out_dev) {
+    const long long n = 2LL * B * N;
+    m->launches++;
+    pos_to_int64_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, c.st>>>(
+        e.pos, n, reinterpret_cast<long long*>(pos_out_dev));
+    STA_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int sta_decode(StaModel* m, const float* feat1_dev, const float* feat2_dev, const int64_t* pos1_dev,
+               const int64_t* pos2_dev, int B, int N, float* const* out1_dev, float* const* out2_dev, void* stream) {
+  RUN(check_ready(m));
+  STA_REQUIRE(B > 0 && N > 0, "empty batch");
+  Ctx c{m, static_cast<cudaStream_t>(stream)};
+  // workspace sized as an (N x 1) token grid: only token counts matter for the decoder buffers
+  RUN(ensure_ws(m, 2 * B, N, 1));
+  DecBufs d = take_dec(m->ws, 2 * B, N);
+  m->launches += 3;
+  RUN(launch_cast_f32_bf16(feat1_dev, d.enc_bf16, static_cast<long long>(B) * N, kEncDim, 0, c.st));
+  RUN(launch_cast_f32_bf16(feat2_dev, d.enc_bf16 + static_cast<size_t>(B) * N * kEncDim, static_cast<long long>(B) * N,
+                           kEncDim, 0, c.st));
+  {
+    const long long total = 2LL * B * (N + 1);
+    build_dec_pos_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, c.st>>>(
+        reinterpret_cast<const long long*>(pos1_dev), reinterpret_cast<const long long*>(pos2_dev), B, N, d.pos);
+    STA_CHECK_CUDA(cudaGetLastError());
+  }
+  return run_decoder(c, B, N, d, out1_dev, out2_dev);
+}
+
+int sta_head_pose(StaModel* m, const float* tok_dev, int B, float* pose_out_dev, float* conf_out_dev, void* stream) {
+  RUN(check_ready(m));
+  m->launches++;
+  return launch_pose_head(tok_dev, kDecDim, B, 0, kLnEps, m->pose, pose_out_dev, conf_out_dev,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int sta_head_pts(StaModel* m, const float* enc_feat_dev, const float* dec6_dev, const float* dec9_dev,
+                 const float* dec12_dev, int B, int H, int W, float* pts3d_out_dev, float* conf_out_dev,
+                 void* stream) {
+  RUN(check_ready(m));
+  STA_REQUIRE(B > 0 && H % 16 == 0 && W % 16 == 0, "image size must be a multiple of 16");
+  Ctx c{m, static_cast<cudaStream_t>(stream)};
+  const int h = H / 16, w = W / 16, N = h * w;
+  RUN(ensure_ws(m, B, h, w));
+  Workspace& ws = m->ws;
+  const size_t T = static_cast<size_t>(B) * N;
+  bf16* k0 = ws.take<bf16>(T * 1024);
+  bf16* k1 = ws.take<bf16>(T * 768);
+  bf16* k2 = ws.take<bf16>(T * 768);
+  bf16* k3 = ws.take<bf16>(T * 768);
+  m->launches += 4;
+  RUN(launch_cast_f32_bf16(enc_feat_dev, k0, T, 1024, 0, c.st));
+  RUN(launch_cast_f32_bf16(dec6_dev, k1, T, 768, 0, c.st));
+  RUN(launch_cast_f32_bf16(dec9_dev, k2, T, 768, 0, c.st));
+  RUN(launch_cast_f32_bf16(dec12_dev, k3, T, 768, 0, c.st));
+  return run_dpt(c, ws, B, h, w, k0, k1, k2, k3, pts3d_out_dev, conf_out_dev);
+}
+
+int sta_forward_pairs(StaModel* m, const void* img1_dev, const void* img2_dev, int img_is_bf16, int B, int H, int W,
+                      float* pts3d_out_dev, float* conf_out_dev, float* pose_out_dev, float* pose_conf_out_dev,
+                      void* stream) {
+  RUN(check_ready(m));
+  STA_REQUIRE(B > 0 && H % 16 == 0 && W % 16 == 0 && H > 0 && W > 0, "image size must be a positive multiple of 16");
+  STA_REQUIRE(H / 16 <= 1024 && W / 16 <= 1024, "token grid exceeds the RoPE table");
+  Ctx c{m, static_cast<cudaStream_t>(stream)};
+  const size_t esz = img_is_bf16 ? 2 : 4;
+  const long long px = static_cast<long long>(H) * W;
+  for (int b0 = 0; b0 < B; b0 += m->max_pairs_per_chunk) {
+    const int nb = (B - b0 < m->max_pairs_per_chunk) ? (B - b0) : m->max_pairs_per_chunk;
+    const char* i1 = static_cast<const char*>(img1_dev) + static_cast<size_t>(b0) * 3 * px * esz;
+    const char* i2 = static_cast<const char*>(img2_dev) + static_cast<size_t>(b0) * 3 * px * esz;
+    RUN(forward_chunk(c, i1, i2, img_is_bf16, nb, H, W, pts3d_out_dev + static_cast<long long>(b0) * px * 3,
+                      conf_out_dev + static_cast<long long>(b0) * px, pose_out_dev + static_cast<long long>(b0) * 16,
+                      pose_conf_out_dev + b0, B));
+  }
+  return 0;
+}
+
+int sta_forward_pairs_host(StaModel* m, const void* img1_host, const void* img2_host, int img_is_bf16, int B, int H,
+                           int W, float* pts3d_out_host, float* conf_out_host, float* pose_out_host,
+                           float* pose_conf_out_host, void* stream) {
+  RUN(check_ready(m));
+  STA_REQUIRE(B > 0 && H % 16 == 0 && W % 16 == 0 && H > 0 && W > 0, "image size must be a positive multiple of 16");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t esz = img_is_bf16 ? 2 : 4;
+  const size_t px = static_cast<size_t>(H) * W;
+  const size_t img_bytes = static_cast<size_t>(B) * 3 * px * esz;
+  const size_t pts_bytes = 2 * static_cast<size_t>(B) * px * 3 * sizeof(float);
+  const size_t conf_bytes = 2 * static_cast<size_t>(B) * px * sizeof(float);
+  const size_t pose_bytes = 2 * static_cast<size_t>(B) * 16 * sizeof(float);
+  const size_t pconf_bytes = 2 * static_cast<size_t>(B) * sizeof(float);
+  auto up = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+  const size_t need = 2 * up(img_bytes) + up(pts_bytes) + up(conf_bytes) + up(pose_bytes) + up(pconf_bytes);
+  if (m->io_bytes < need) {
+    STA_CHECK_CUDA(cudaDeviceSynchronize());
+    if (m->io) STA_CHECK_CUDA(cudaFree(m->io));
+    m->io = nullptr;
+    m->io_bytes = 0;
+    STA_CHECK_CUDA(cudaMalloc(&m->io, need));
+    m->io_bytes = need;
+  }
+  char* p = m->io;
+  char* d_img1 = p; p += up(img_bytes);
+  char* d_img2 = p; p += up(img_bytes);
+  float* d_pts = reinterpret_cast<float*>(p); p += up(pts_bytes);
+  float* d_conf = reinterpret_cast<float*>(p); p += up(conf_bytes);
+  float* d_pose = reinterpret_cast<float*>(p); p += up(pose_bytes);
+  float* d_pconf = reinterpret_cast<float*>(p);
+  STA_CHECK_CUDA(cudaMemcpyAsync(d_img1, img1_host, img_bytes, cudaMemcpyHostToDevice, st));
+  STA_CHECK_CUDA(cudaMemcpyAsync(d_img2, img2_host, img_bytes, cudaMemcpyHostToDevice, st));
+  RUN(sta_forward_pairs(m, d_img1, d_img2, img_is_bf16, B, H, W, d_pts, d_conf, d_pose, d_pconf, stream));
+  STA_CHECK_CUDA(cudaMemcpyAsync(pts3d_out_host, d_pts, pts_bytes, cudaMemcpyDeviceToHost, st));
+  STA_CHECK_CUDA(cudaMemcpyAsync(conf_out_host, d_conf, conf_bytes, cudaMemcpyDeviceToHost, st));
+  STA_CHECK_CUDA(cudaMemcpyAsync(pose_out_host, d_pose, pose_bytes, cudaMemcpyDeviceToHost, st));
+  STA_CHECK_CUDA(cudaMemcpyAsync(pose_conf_out_host, d_pconf, pconf_bytes, cudaMemcpyDeviceToHost, st));
+  STA_CHECK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// op-level entry points (parity tests drive the same kernels the model uses)
+// ---------------------------------------------------------------------------
+int sta_op_gemm(const StaGemmDesc* d, void* stream) {
+  if (!d) {
+    set_last_error("sta_op_gemm: null descriptor");
+    return 2;
+  }
+  GemmLaunch g;
+  g.amode = d->conv3x3 ? A_CONV3 : A_LINEAR;
+  g.epi = d->epi;
+  g.A = static_cast<const bf16*>(d->A);
+  g.lda = d->lda;
+  g.Wt = static_cast<const bf16*>(d->W);
+  g.ldw = d->ldw;
+  GemmParams p = {};
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.nimg = d->nimg; p.H = d->H; p.W = d->Wd; p.Cin = d->Cin;
+  p.bias = d->bias;
+  p.out = d->out; p.ldo = d->ldo; p.out2 = d->out2;
+  p.resid = d->resid; p.resid2 = d->resid2;
+  p.relu_main = d->relu_main;
+  p.rowmap_n = d->rowmap_n;
+  p.pos = d->pos; p.rope_cols = d->rope_cols;
+  if (d->epi == EPI_ROPE) {
+    p.rope_tab = rope_table(&p.rope_max_pos);
+    if (!p.rope_tab) {
+      set_last_error("failed to build the RoPE table");
+      return 1;
+    }
+  }
+  p.ps_k = d->ps_k; p.ps_cout = d->ps_cout; p.ps_h = d->ps_h; p.ps_w = d->ps_w;
+  p.head_w = d->head_w; p.head_b = d->head_b; p.pts3d = d->pts3d; p.conf = d->conf;
+  g.p = p;
+  return launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
+int sta_op_attention(const void* q, int64_t ldq, int q_col0, const void* k, int64_t ldk, int k_col0, const void* v,
+                     int64_t ldv, int v_col0, void* out, int64_t ldo, int batch, int heads, int nq, int nk,
+                     int kv_batch_shift, float scale, void* stream) {
+  AttnLaunch a;
+  a.q = static_cast<const bf16*>(q); a.ldq = ldq; a.q_col0 = q_col0;
+  a.k = static_cast<const bf16*>(k); a.ldk = ldk; a.k_col0 = k_col0;
+  a.v = static_cast<const bf16*>(v); a.ldv = ldv; a.v_col0 = v_col0;
+  a.out = static_cast<bf16*>(out); a.ldo = ldo;
+  a.batch = batch; a.heads = heads; a.nq = nq; a.nk = nk;
+  a.kv_batch_shift = kv_batch_shift;
+  a.scale = scale;
+  return launch_attention(a, static_cast<cudaStream_t>(stream));
+}
+
+int sta_op_layernorm(const float* x, int rows, int C, float eps, const float* g1, const float* b1, void* out1_bf16,
+                     const float* g2, const float* b2, void* out2_bf16, int drop_first_of, void* stream) {
+  return launch_layernorm(x, rows, C, eps, g1, b1, static_cast<bf16*>(out1_bf16), g2, b2,
+                          static_cast<bf16*>(out2_bf16), drop_first_of, static_cast<cudaStream_t>(stream));
+}
+int sta_op_patch_im2col(const void* img, int img_is_bf16, int B, int H, int W, void* out_bf16, void* stream) {
+  return launch_patch_im2col(img, img_is_bf16, B, H, W, static_cast<bf16*>(out_bf16), static_cast<cudaStream_t>(stream));
+}
+int sta_op_upsample2x(const void* in_bf16, void* out_bf16, int nimg, int H, int W, int C, void* stream) {
+  return launch_upsample2x(static_cast<const bf16*>(in_bf16), static_cast<bf16*>(out_bf16), nimg, H, W, C, 2 * H, 2 * W,
+                           static_cast<cudaStream_t>(stream));
+}
+int sta_op_im2col_3x3_s2(const void* in_bf16, void* out_bf16, int nimg, int H, int W, int C, void* stream) {
+  return launch_im2col_3x3_s2(static_cast<const bf16*>(in_bf16), static_cast<bf16*>(out_bf16), nimg, H, W, C,
+                              static_cast<cudaStream_t>(stream));
+}
+int sta_op_cast_f32_bf16(const float* in, void* out_bf16, int64_t rows, int C, int drop_first_of, void* stream) {
+  return launch_cast_f32_bf16(in, static_cast<bf16*>(out_bf16), rows, C, drop_first_of,
+                              static_cast<cudaStream_t>(stream));
+}
+int sta_op_rope2d(void* tokens_bf16, const int64_t* pos, int B, int N, int H, void* stream) {
+  return launch_rope2d(static_cast<bf16*>(tokens_bf16), reinterpret_cast<const long long*>(pos), B, N, H,
+                       static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
