@@ -98,6 +98,13 @@ int64_t sta_launch_count(StaModel* m);
 /* Bytes of device memory currently held (weights + workspace). */
 int64_t sta_device_bytes(StaModel* m);
 
+/* Per-kernel-family device timing with CUDA events on the launch stream (adds two event records per
+ * launch while enabled).  Families: 0 = tcgen05 GEMM (linear), 1 = tcgen05 GEMM (implicit 3x3 conv),
+ * 2 = attention, 3 = LayerNorm.  sta_profile_read synchronises, returns the accumulated milliseconds,
+ * launch counts and executed FLOPs per family since the last read, and resets the counters. */
+int sta_profile(StaModel* m, int enable);
+int sta_profile_read(StaModel* m, double* ms4, int64_t* counts4, double* flops4);
+
 /* ---- op-level entry points (used by the parity tests; same kernels the model uses) ---- */
 
 enum { STA_EPI_BF16 = 0, STA_EPI_GELU = 1, STA_EPI_F32 = 2, STA_EPI_ROPE = 3, STA_EPI_PIXSHUF = 4, STA_EPI_HEAD = 5 };

@@ -66,6 +66,8 @@ def lib():
     L.sta_launch_count.restype = i64
     L.sta_device_bytes.argtypes = [vp]
     L.sta_device_bytes.restype = i64
+    L.sta_profile.argtypes = [vp, i]
+    L.sta_profile_read.argtypes = [vp, POINTER(ctypes.c_double), POINTER(c_int64), POINTER(ctypes.c_double)]
     L.sta_op_gemm.argtypes = [POINTER(StaGemmDesc), vp]
     L.sta_op_attention.argtypes = [vp, i64, i, vp, i64, i, vp, i64, i, vp, i64, i, i, i, i, i, c_float, vp]
     L.sta_op_layernorm.argtypes = [vp, i, i, c_float, vp, vp, vp, vp, vp, vp, i, vp]

@@ -186,6 +186,25 @@ struct StaModel {
   int64_t launches = 0;
   int max_pairs_per_chunk = 16;
 
+  // ---- optional per-kernel-family timing (CUDA events on the launch stream) ----
+  bool prof_on = false;
+  struct ProfRec { int cat; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[4] = {0, 0, 0, 0};
+  int64_t prof_cnt[4] = {0, 0, 0, 0};
+  double prof_flops[4] = {0, 0, 0, 0};
+  cudaEvent_t prof_event() {
+    cudaEvent_t e;
+    if (!prof_pool.empty()) {
+      e = prof_pool.back();
+      prof_pool.pop_back();
+    } else {
+      cudaEventCreate(&e);
+    }
+    return e;
+  }
+
   template <typename T>
   T* alloc(size_t n) {
     arena_off = (arena_off + 255) & ~static_cast<size_t>(255);
@@ -369,6 +388,27 @@ struct Ctx {
   cudaStream_t st;
 };
 
+enum ProfCat { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN = 2, PROF_LN = 3 };
+// RAII scope: records an event pair around one launch when profiling is enabled
+struct ProfScope {
+  StaModel* m;
+  cudaStream_t st;
+  int cat;
+  cudaEvent_t e0 = nullptr;
+  ProfScope(const Ctx& c, int cat_, double flops) : m(c.m), st(c.st), cat(cat_) {
+    if (!m->prof_on) return;
+    m->prof_flops[cat] += flops;
+    e0 = m->prof_event();
+    cudaEventRecord(e0, st);
+  }
+  ~ProfScope() {
+    if (!e0) return;
+    cudaEvent_t e1 = m->prof_event();
+    cudaEventRecord(e1, st);
+    m->prof_recs.push_back({cat, e0, e1});
+  }
+};
+
 int gemm(const Ctx& c, int amode, int epi, const bf16* A, long long lda, const Lin& L, GemmParams p) {
   GemmLaunch g;
   g.amode = amode;
@@ -382,6 +422,8 @@ int gemm(const Ctx& c, int amode, int epi, const bf16* A, long long lda, const L
   if (!p.bias) p.bias = L.b;
   g.p = p;
   c.m->launches++;
+  const double rows = (amode == A_CONV3) ? static_cast<double>(p.nimg) * p.H * p.W : static_cast<double>(p.M);
+  ProfScope ps(c, amode == A_CONV3 ? PROF_CONV : PROF_GEMM, 2.0 * rows * L.N * L.K);
   return launch_gemm(g, c.st);
 }
 // plain linear on rows
@@ -422,6 +464,7 @@ int conv3(const Ctx& c, const bf16* in, int nimg, int H, int W, int Cin, const L
 int ln(const Ctx& c, const float* x, int rows, int C, const LNp& a, bf16* out1, const LNp* b2 = nullptr,
        bf16* out2 = nullptr, int drop_first_of = 0) {
   c.m->launches++;
+  ProfScope ps(c, PROF_LN, 0.0);
   return launch_layernorm(x, rows, C, kLnEps, a.g, a.b, out1, b2 ? b2->g : nullptr, b2 ? b2->b : nullptr, out2,
                           drop_first_of, c.st);
 }
@@ -436,6 +479,7 @@ int attn(const Ctx& c, const bf16* q, long long ldq, int qc, const bf16* k, long
   a.kv_batch_shift = shift;
   a.scale = 0.125f;  // head_dim ** -0.5, sta_blocks.py:86
   c.m->launches++;
+  ProfScope ps(c, PROF_ATTN, 4.0 * batch * heads * static_cast<double>(nq) * nk * 64);
   return launch_attention(a, c.st);
 }
 
@@ -830,6 +874,11 @@ void sta_destroy(StaModel* m) {
   if (m->ws.base) cudaFree(m->ws.base);
   if (m->stage) cudaFree(m->stage);
   if (m->io) cudaFree(m->io);
+  for (auto& r : m->prof_recs) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  for (auto e : m->prof_pool) cudaEventDestroy(e);
   delete m;
 }
 
@@ -837,6 +886,37 @@ int sta_missing_tensors(StaModel* m) { return m ? m->missing : -1; }
 int64_t sta_launch_count(StaModel* m) { return m ? m->launches : 0; }
 int64_t sta_device_bytes(StaModel* m) {
   return m ? static_cast<int64_t>(m->arena_bytes + m->ws.bytes + m->stage_bytes + m->io_bytes) : 0;
+}
+int sta_profile(StaModel* m, int enable) {
+  if (!m) return 2;
+  m->prof_on = enable != 0;
+  return 0;
+}
+int sta_profile_read(StaModel* m, double* ms4, int64_t* counts4, double* flops4) {
+  if (!m || !ms4 || !counts4 || !flops4) {
+    set_last_error("sta_profile_read: null argument");
+    return 2;
+  }
+  STA_CHECK_CUDA(cudaDeviceSynchronize());
+  for (auto& r : m->prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      m->prof_ms[r.cat] += ms;
+      m->prof_cnt[r.cat]++;
+    }
+    m->prof_pool.push_back(r.e0);
+    m->prof_pool.push_back(r.e1);
+  }
+  m->prof_recs.clear();
+  for (int i = 0; i < 4; ++i) {
+    ms4[i] = m->prof_ms[i];
+    counts4[i] = m->prof_cnt[i];
+    flops4[i] = m->prof_flops[i];
+    m->prof_ms[i] = 0;
+    m->prof_cnt[i] = 0;
+    m->prof_flops[i] = 0;
+  }
+  return 0;
 }
 int sta_weight_arena(StaModel* m, void** ptr, int64_t* bytes) {
   if (!m || !ptr || !bytes) {
