@@ -1,0 +1,319 @@
+"""STA image-pairs/s benchmark (BASELINE.json metric) -- contract: see the task statement / DESIGN.md.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--pairs P] [--height H] [--width W]
+
+* b200 arm (default): one process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE).  Rank 0 initialises the
+  weights, one NCCL broadcast of the packed weight arena, then every rank runs `--pairs` synthetic
+  512x384 bf16 pairs per step, independently (weak scaling, no data-path collective).
+  `value`   = whole-job pairs/s with the inputs resident in HBM (CUDA events, max over ranks).
+  `e2e`     = the same metric through the host-buffer C-ABI call sta_forward_pairs_host: pinned-host ->
+              device copies of both image batches and device -> host copies of all four outputs are
+              inside the timed region.
+  `roofline`= tensor-pipe roofline of the dominant kernel family (tcgen05 GEMM / implicit-GEMM conv),
+              timed live with CUDA events on the launch stream (sta_profile).
+  `cpu_baseline` = the oracle (PyTorch fp32 CPU port of the reference, oracle/sta_oracle.py) timed on the
+              host cores on a bounded sample (rank 0, N=1 only).
+* reference arm (`--impl reference`): the reference's own CPU implementation of the path = the oracle
+  port (a Python reference cannot travel to the GPU box), all host threads, one 512x384 pair per step.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sta_image_pairs_per_sec"
+UNIT = "pairs/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_burst": d.get("bf16_tflops"), "bf16_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_baseline(H, W):
+    """Time the oracle (fp32 CPU port of the reference path) on a bounded sample of the workload.
+    A 224x224 pair (435.8 GF) is timed first; the full-size pair (1857.5 GF at 512x384) only if the probe
+    says it fits in ~40 s, otherwise the probe is FLOP-scaled and reported as such."""
+    import torch
+
+    from oracle.sta_oracle import StaOracle, flops_per_pair, make_images, make_state_dict, usable_cpus
+    torch.set_num_threads(usable_cpus())
+    cores = torch.get_num_threads()
+    orc = StaOracle(make_state_dict(0), emulate_bf16=False)
+    with torch.no_grad():
+        a, b = make_images(1, 64, 80, 1)
+        orc.forward_pair(a, b)  # warm-up
+        a, b = make_images(1, 224, 224, 1234)
+        t0 = time.perf_counter()
+        orc.forward_pair(a, b)
+        t_probe = time.perf_counter() - t0
+        ratio = flops_per_pair(H, W) / flops_per_pair(224, 224)
+        if t_probe * ratio > 40.0:
+            return {"value": 1.0 / (t_probe * ratio), "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": "one 224x224 pair (%.1f s), FLOP-scaled x%.2f to %dx%d" % (t_probe, ratio, W, H)}
+        a, b = make_images(1, H, W, 1234)
+        t0 = time.perf_counter()
+        orc.forward_pair(a, b)
+        t_full = time.perf_counter() - t0
+    return {"value": 1.0 / t_full, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "one %dx%d pair fp32 (%.1f s of CPU work) after a 224x224 probe (%.1f s)" % (W, H, t_full, t_probe)}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    H, W = args.height, args.width
+    import torch
+
+    from oracle.sta_oracle import StaOracle, make_images, make_state_dict, usable_cpus
+    torch.set_num_threads(usable_cpus())
+    orc = StaOracle(make_state_dict(0), emulate_bf16=False)
+    img1, img2 = make_images(1, H, W, 1234)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            orc.forward_pair(img1, img2)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            orc.forward_pair(img1, img2)
+        dt = time.perf_counter() - t0
+    v = args.steps / dt
+    cores = torch.get_num_threads()
+    line = {
+        "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "cfg-2 shape: synthetic %dx%d pairs, STA forward only (2 enc + sym. dec + 2 DPT + 2 pose); "
+                               "reference CPU path = oracle port, 1 pair per step (bounded sample)" % (W, H),
+                   "pairs_per_step": 1, "height": H, "width": W},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d timed single-pair forwards at %dx%d fp32, %d threads" % (args.steps, W, H, cores)},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200_arm(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from vista_slam_b200.flops import attention_flops_per_pair, flops_per_pair
+    from vista_slam_b200 import _lib
+    from vista_slam_b200.sta_model.sta_model import SymmetricTwoViewAssociation as STA
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    H, W, P = args.height, args.width, args.pairs
+    model = STA()  # random-init weights of the reference architecture (no network for the checkpoint)
+    model.eval()
+    if world > 1:
+        model.broadcast_weights(src=0, device=dev)  # one NCCL broadcast of the packed arena over NVLink
+    else:
+        model._ready(torch.empty(1, device=dev))
+    g = torch.Generator().manual_seed(1234 + rank)
+    h1 = (torch.rand(P, 3, H, W, generator=g) * 2 - 1).bfloat16().pin_memory()
+    h2 = (torch.rand(P, 3, H, W, generator=g) * 2 - 1).bfloat16().pin_memory()
+    d1, d2 = h1.to(dev), h2.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for _ in range(args.warmup):
+        model.forward_pairs(d1, d2)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = model.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = model.forward_pairs(d1, d2)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = model.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = world * P / (ms_step / 1e3)
+    ok = bool(torch.isfinite(out[0]["pts3d_pred"]).all()) and bool(torch.isfinite(out[1]["relative_pose"]).all())
+
+    # ---------------- end-to-end through the host-buffer C-ABI call (`e2e`) ----------------
+    hout = {"pts3d": torch.empty(2, P, H, W, 3).pin_memory(), "conf": torch.empty(2, P, H, W).pin_memory(),
+            "pose": torch.empty(2, P, 4, 4).pin_memory(), "pose_conf": torch.empty(2, P).pin_memory()}
+    for _ in range(max(1, min(args.warmup, 2))):
+        model.forward_pairs_host(h1, h2, hout)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        model.forward_pairs_host(h1, h2, hout)  # H2D + forward + D2H + stream sync inside
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)) / args.steps
+    e2e_value = world * P / (e2e_ms / 1e3)
+    h2d = 2 * h1.numel() * h1.element_size()
+    d2h = sum(t.numel() * t.element_size() for t in hout.values())
+
+    # ---------------- roofline of the dominant kernel family (live CUDA-event timing) ----------------
+    L = _lib.lib()
+    L.sta_profile(model._handle, 1)
+    prof_steps = min(args.steps, 3)
+    for _ in range(prof_steps):
+        model.forward_pairs(d1, d2)
+    ms4, cnt4, fl4 = (ctypes.c_double * 4)(), (ctypes.c_int64 * 4)(), (ctypes.c_double * 4)()
+    _lib.check(L.sta_profile_read(model._handle, ms4, cnt4, fl4))
+    L.sta_profile(model._handle, 0)
+    peaks = load_peaks()
+    flop_pair = flops_per_pair(H, W)
+    # algorithmic FLOPs handled by the GEMM family per pair = total - attention
+    attn_flops_pair = attention_flops_per_pair(H, W)
+    gemm_flops_pair = flop_pair - attn_flops_pair
+    gemm_ms = (ms4[0] + ms4[1]) / prof_steps
+    gemm_launches = (cnt4[0] + cnt4[1]) // prof_steps
+    achieved = P * gemm_flops_pair / (gemm_ms / 1e3) / 1e12
+    peak = peaks["bf16_sustained"] or peaks["bf16_burst"]
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM 3x3 conv family)",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peaks["source"] + ", sustained cuBLAS bf16 (kernel timed inside a long step)",
+        "launches_per_step": int(gemm_launches), "avg_launch_ms": gemm_ms / max(1, gemm_launches),
+        "algorithmic_gflop_per_launch_avg": P * gemm_flops_pair / max(1, gemm_launches) / 1e9,
+        "family_ms_per_step": {"gemm_linear": ms4[0] / prof_steps, "gemm_conv3x3": ms4[1] / prof_steps,
+                               "attention": ms4[2] / prof_steps, "layernorm": ms4[3] / prof_steps},
+        "attention_tflops": P * attn_flops_pair / (ms4[2] / prof_steps / 1e3) / 1e12 if ms4[2] > 0 else None,
+        "whole_step_tflops": value * flop_pair / 1e12 / world,
+        "whole_step_frac": value * flop_pair / 1e12 / world / peak,
+    }
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_port_baseline(H, W)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "impl": "b200",
+            "config": {"workload": "cfg-2: %d synthetic %dx%d bf16 pairs per GPU per step, STA forward only "
+                                   "(2 enc + symmetric dec + 2 DPT + 2 pose heads per pair), random-init weights" % (P, W, H),
+                       "pairs_per_gpu": P, "global_pairs": P * world, "height": H, "width": W,
+                       "parallelism": "pair shard per rank, 1 NCCL weight broadcast, no data-path collective",
+                       "l2_policy": "no explicit flush: per-step working set (0.88 GB weights + >2 GB activations) "
+                                    "exceeds the 126 MB L2",
+                       "gflop_per_pair": flop_pair / 1e9},
+            "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                      "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "outputs_finite": ok,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=16, help="pairs per GPU per step (cfg-2: 16)")
+    ap.add_argument("--height", type=int, default=384)
+    ap.add_argument("--width", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            # convenience: re-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                   "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+    run_b200_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -110,8 +110,38 @@ def make_state_dict(seed=0, dtype=torch.float32):
                 for v in shape[1:]:
                     fan_in *= v
             t = torch.randn(shape, generator=g) / math.sqrt(fan_in)
+            if name.endswith("head.4.weight"):
+                # keep |xyz| (= log1p of the point distance, postprocess.py:37-48) and the confidence logit
+                # in the O(1) range of a trained model instead of the O(10) a variance-preserving init gives
+                t = t * 0.1
         sd[name] = t.to(dtype)
     return sd
+
+
+def usable_cpus(cap=32):
+    """Threads the CPU legs may use: CPU affinity and cgroup quota, not os.cpu_count() (a 128-core host whose
+    container is limited to a few cores thrashes badly when torch spawns 128 threads)."""
+    import os
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+            break
+        except Exception:
+            continue
+    return max(1, min(n, cap))
 
 
 def make_images(B, H, W, seed=1234):

@@ -20,7 +20,7 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
-from oracle.sta_oracle import StaOracle, make_images, make_state_dict  # noqa: E402
+from oracle.sta_oracle import usable_cpus, StaOracle, make_images, make_state_dict  # noqa: E402
 from ref_import import import_reference_sta  # noqa: E402
 
 CASES = [
@@ -35,7 +35,7 @@ def maxrel(a, b):
 
 
 def main():
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(usable_cpus())
     STA = import_reference_sta()
     t0 = time.time()
     sd = make_state_dict(0)

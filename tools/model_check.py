@@ -14,7 +14,7 @@ import torch
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
 
-from oracle.sta_oracle import StaOracle, flops_per_pair, make_images, make_state_dict  # noqa: E402
+from oracle.sta_oracle import usable_cpus, StaOracle, flops_per_pair, make_images, make_state_dict  # noqa: E402
 from vista_slam_b200 import _lib  # noqa: E402
 from vista_slam_b200.sta_model.sta_model import SymmetricTwoViewAssociation as STA  # noqa: E402
 
@@ -29,7 +29,7 @@ def nrm(a, b):
 
 
 def main():
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(usable_cpus())
     t0 = time.time()
     sd = make_state_dict(0)
     print("weights %.1fs, cpu threads %d" % (time.time() - t0, torch.get_num_threads()), flush=True)
