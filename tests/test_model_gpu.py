@@ -19,9 +19,11 @@ from oracle.sta_oracle import StaOracle, make_images
 
 pytestmark = pytest.mark.gpu
 
-# (a) vs oracle-bf16emu, (b) vs fp32 reference golden
-TOL_EMU = {"pts3d_pred": 3e-2, "conf": 3e-2, "relative_pose": 1e-2, "relative_pose_conf": 5e-3}
-TOL_FP32 = {"pts3d_pred": 2e-1, "conf": 2e-1, "relative_pose": 5e-2, "relative_pose_conf": 2e-2}
+# Max-normalised bounds, set at ~3x the deviations measured on B200 in round 1 (profiles/r01_model_check*.log:
+# trunk features 6e-3..9e-3, pose 2e-3..1.8e-2, pts3d/conf 1e-2..2e-2 at |xyz| <= 3, pose_conf <= 2e-3).
+# (a) vs oracle-bf16emu, (b) vs fp32 reference golden / fp32 oracle.
+TOL_EMU = {"pts3d_pred": 5e-2, "conf": 5e-2, "relative_pose": 4e-2, "relative_pose_conf": 5e-3}
+TOL_FP32 = {"pts3d_pred": 1e-1, "conf": 1e-1, "relative_pose": 5e-2, "relative_pose_conf": 1e-2}
 
 
 def maxn(a, b):
