@@ -3,23 +3,48 @@
 #include "host_util.h"
 #include "ops.h"
 
+#include <stdlib.h>
+
 namespace sta {
 
-template <int BN, int AMODE, int EPI>
+template <int BN, int AMODE, int EPI, int CG>
 static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_tiles,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tc_kernel<BN, AMODE, EPI>;
+  using Cfg = GemmCfg<BN, CG>;
+  auto kern = gemm_tc_kernel<BN, AMODE, EPI, CG>;
   static bool attr_set = false;
   if (!attr_set) {
     STA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  if (grid < 1) return 0;
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-  STA_CHECK_CUDA(cudaGetLastError());
+  // persistent: one CTA (CG=1) or one CTA pair (CG=2) per work-item slot
+  const int max_items = num_sms() / CG;
+  const int items = num_tiles < max_items ? num_tiles : max_items;
+  if (items < 1) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(items * CG);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  STA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   return 0;
+}
+
+// STA_GEMM_CTA_GROUP=1 forces the single-CTA kernels (A/B timing and debugging)
+static int cta_group_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("STA_GEMM_CTA_GROUP");
+    mode = (e && e[0] == '1') ? 1 : 2;
+  }
+  return mode;
 }
 
 int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
@@ -32,6 +57,7 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
   // BN = 256 for the wide trunk layers, 128 when N is not a multiple of 256.
   const int bn = (p.N % 256 == 0 && g.epi != EPI_PIXSHUF && g.epi != EPI_HEAD) ? 256 : 128;
 
+  const int cg = cta_group_mode();
   CUtensorMap tmA, tmB;
   int m_tiles;
   if (g.amode == A_CONV3) {
@@ -57,14 +83,17 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
     STA_REQUIRE(g.ldw % 8 == 0, "ldw must be a multiple of 8 elements (16 bytes)");
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
     uint64_t strides[1] = {(uint64_t)g.ldw * 2};
-    uint32_t box[2] = {64, (uint32_t)bn};
+    uint32_t box[2] = {64, (uint32_t)(bn / cg)};
     if (make_tmap_bf16(&tmB, g.Wt, 2, dims, strides, box)) return 1;
   }
   const int n_tiles = (p.N + bn - 1) / bn;
-  const int num_tiles = m_tiles * n_tiles;
+  const int num_tiles = ((m_tiles + cg - 1) / cg) * n_tiles;
 
-#define STA_GEMM_CASE(BN_, AM_, EP_) \
-  if (bn == BN_ && g.amode == AM_ && g.epi == EP_) return launch_inst<BN_, AM_, EP_>(tmA, tmB, p, num_tiles, stream);
+#define STA_GEMM_CASE(BN_, AM_, EP_)                                                   \
+  if (bn == BN_ && g.amode == AM_ && g.epi == EP_) {                                   \
+    if (cg == 2) return launch_inst<BN_, AM_, EP_, 2>(tmA, tmB, p, num_tiles, stream); \
+    return launch_inst<BN_, AM_, EP_, 1>(tmA, tmB, p, num_tiles, stream);              \
+  }
 
   STA_GEMM_CASE(256, A_LINEAR, EPI_BF16)
   STA_GEMM_CASE(256, A_LINEAR, EPI_GELU)

@@ -740,11 +740,14 @@ int run_dpt(const Ctx& c, Workspace& ws, int nimg, int h, int w, const bf16* hoo
     RUN(conv3(c, s_relu, nimg, Hh, Ww, 256, r.r2.c1, b.t2, nullptr, nullptr, nullptr, 1));
     RUN(conv3(c, b.t2, nimg, Hh, Ww, 256, r.r2.c2, b.o, nullptr, s_raw, nullptr, 0));
     // bilinear x2 (align_corners=True), cropped to the next level's size for refinenet4 (dpt_head.py:58)
+    // The reference applies out_conv (1x1) AFTER the upsample (dpt_block.py:215-217).  Both are linear and the
+    // bilinear weights sum to one, so conv1x1(up(x)) == up(conv1x1(x)) exactly in real arithmetic; doing the
+    // 1x1 at the low resolution costs a quarter of the FLOPs and HBM bytes.
     int OH = 2 * Hh, OW = 2 * Ww;
     if (lvl == 3) { OH = LH[2]; OW = LW[2]; }
+    RUN(linear(c, EPI_BF16, b.o, nimg * Hh * Ww, r.out, b.up));
     m->launches++;
-    RUN(launch_upsample2x(b.o, b.up, nimg, Hh, Ww, 256, OH, OW, c.st));
-    RUN(linear(c, EPI_BF16, b.up, nimg * OH * OW, r.out, b.path));
+    RUN(launch_upsample2x(b.up, b.path, nimg, Hh, Ww, 256, OH, OW, c.st));
     path = b.path;
   }
   // ---- head (dpt_block.py:318-324) + postprocess (postprocess.py:10-62) ----
