@@ -6,104 +6,152 @@
 //   * the materialised softmax(q k^T * scale) v of CrossAttention, sta_blocks.py:201-205
 //     (K/V taken from the partner sample: kv_batch_shift).
 //
-// Q, K, V are read straight out of the projection GEMM outputs with 3-D TMA
-// tensor maps (64 head columns x tokens x samples); nothing is re-laid-out.
-//   S = Q K^T        tcgen05.mma 128x128x64, K-major A and B, fp32 in TMEM
-//   P = exp2(S*c - m) in registers (one query row per thread), written as bf16
-//       into a 128B-swizzled K-major smem tile
-//   O_j = P V_j      tcgen05.mma 128x64x128, V consumed MN-major exactly as TMA wrote it
-//   running (m, l, O) rescaling in fp32 registers.
-// Two CTAs fit per SM (112 KB smem, 256 TMEM columns) so one CTA's softmax
-// overlaps the other's MMAs.
+// Q, K, V are read straight out of the projection GEMM outputs with 3-D TMA tensor maps
+// (64 head columns x tokens x samples); nothing is re-laid-out.
+//
+// Pipeline (persistent; a CTA walks work items = (pair of 128-query tiles, head, sample); 384 threads,
+// setmaxnreg moves registers from the TMA/MMA warpgroup to the two softmax warpgroups):
+//   warp 0      TMA producer: the two Q tiles of the item (double buffered across items), K tiles and V tiles
+//               of 128 keys (3 stages each) -- K/V are shared by the two query tiles
+//   warp 1      MMA issuer (one elected thread), per key tile n and query tile t in {A, B}:
+//               S_t = Q_t K_n^T (128x128x64, fp32 in TMEM), O_t += P_t V_n (128x64x128 accumulating in TMEM,
+//               V consumed MN-major exactly as TMA wrote it)
+//   warps 4..7  softmax group A (query tile 2i), warps 8..11 group B (query tile 2i+1): one thread per query
+//               row.  The 128 scores of the row are read from TMEM ONCE into registers, which frees the S
+//               buffer at once (the next Q K^T overlaps the softmax); P = exp2(S*c - m) goes to a
+//               128B-swizzled K-major bf16 smem tile.  O stays in TMEM: the running maximum used for the
+//               exponentials is only raised when the true maximum exceeds it by more than 2^8 (exact after
+//               the final division by l, P <= 256 in between), so O has to be rescaled in place
+//               (tcgen05.ld / st) only on the rare tiles where that happens.
+// The two groups are independent streams sharing K/V; group B starts half a period late so that one group's
+// exp2 (MUFU-bound) phase overlaps the other's load / max / store phases.
 #include "common.cuh"
 #include "host_util.h"
 #include "ops.h"
+
+#include <stdlib.h>
 
 namespace sta {
 
 namespace {
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 384;  // warpgroup 0: TMA / MMA / 2 idle warps; warpgroups 1, 2: softmax groups A, B
+constexpr int KV_STAGES = 3;
 constexpr uint32_t TILE_BYTES = 128 * 64 * 2;  // 16 KB: [128 rows][64 bf16]
-constexpr uint32_t ATT_SMEM = TILE_BYTES * (1 + 2 + 2 + 2) + 256;
+// Q [group][2 buffers] | K x3 | V x3 | P [group] (two 64-key sub-tiles each) | barriers
+constexpr uint32_t ATT_OFF_K = 4 * TILE_BYTES;
+constexpr uint32_t ATT_OFF_V = ATT_OFF_K + KV_STAGES * TILE_BYTES;
+constexpr uint32_t ATT_OFF_P = ATT_OFF_V + KV_STAGES * TILE_BYTES;
+constexpr uint32_t ATT_OFF_BAR = ATT_OFF_P + 4 * TILE_BYTES;
+constexpr uint32_t ATT_SMEM = ATT_OFF_BAR + 256;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 struct AttnParams {
-  int nq, nk, batch, kv_batch_shift;
+  int nq, nk, batch, heads, qpairs, kv_batch_shift;
+  int nitems;
   float scale_log2;
   __nv_bfloat16* out;
   long long ldo;
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const AttnParams p, int q_col0, int k_col0,
-                     int v_col0) {
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                     const AttnParams p, int q_col0, int k_col0, int v_col0) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + TILE_BYTES;       // 2 stages
-  uint8_t* sV = smem + 3 * TILE_BYTES;   // 2 stages
-  uint8_t* sP = smem + 5 * TILE_BYTES;   // 2 sub-tiles of 64 keys
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * TILE_BYTES);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* v_full = bars + 3;   // [2]
-  uint64_t* k_empty = bars + 5;  // [2]
-  uint64_t* v_empty = bars + 7;  // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* p_full = bars + 10;
-  uint64_t* o_full = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint8_t* sQ = smem;  // group t, buffer b at sQ + (2 * t + b) * TILE_BYTES
+  uint8_t* sK = smem + ATT_OFF_K;
+  uint8_t* sV = smem + ATT_OFF_V;
+  uint8_t* sP = smem + ATT_OFF_P;  // group t at sP + t * 2 * TILE_BYTES
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_OFF_BAR);
+  uint64_t* q_full = bars + 0;    // [2 groups][2 buffers]
+  uint64_t* q_empty = bars + 4;   // [2][2]
+  uint64_t* k_full = bars + 8;    // [3]
+  uint64_t* k_empty = bars + 11;  // [3]
+  uint64_t* v_full = bars + 14;   // [3]
+  uint64_t* v_empty = bars + 17;  // [3]
+  uint64_t* s_full = bars + 20;   // [2]  MMA -> softmax group t: S_t ready
+  uint64_t* s_free = bars + 22;   // [2]  softmax group t -> MMA: S_t is in registers, buffer reusable
+  uint64_t* p_full = bars + 24;   // [2]  softmax group t -> MMA: P_t written (and O_t rescaled if needed)
+  uint64_t* o_full = bars + 26;   // [2]  MMA -> softmax group t: O_t += P_t V done (P_t consumed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int kvb = (b + p.kv_batch_shift) % p.batch;
   const int T = (p.nk + 127) / 128;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) device_fatal("dynamic shared memory is not 1024-byte aligned");
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
+    for (int i = 0; i < KV_STAGES; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&v_full[i], 1);
       mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
-    mbar_init(o_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + 128;
+  // columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
 
+
+  auto decode = [&](int w, int& q0, int& head, int& b, int& kvb) {
+    const int qp = w % p.qpairs;
+    const int rest = w / p.qpairs;
+    head = rest % p.heads;
+    b = rest / p.heads;
+    q0 = qp * 256;
+    kvb = (b + p.kv_batch_shift) % p.batch;
+  };
+  const int my_items = (p.nitems > static_cast<int>(blockIdx.x))
+                           ? (p.nitems - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
+                           : 0;
+
+  // register re-distribution: the softmax threads keep a whole 128-score row in registers
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
-      mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(sQ, &tmQ, q_full, q_col0 + head * 64, q0, b);
-      for (int j = 0; j < T; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
-        tma_load_3d(sK + st * TILE_BYTES, &tmK, &k_full[st], k_col0 + head * 64, j * 128, kvb);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
-        tma_load_3d(sV + st * TILE_BYTES, &tmV, &v_full[st], v_col0 + head * 64, j * 128, kvb);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_items; ++it) {
+        int q0, head, b, kvb;
+        decode(static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x), q0, head, b, kvb);
+        const int qb = it & 1;
+        for (int t = 0; t < 2; ++t) {  // a second tile beyond nq is zero-filled by TMA (and never stored)
+          mbar_wait(&q_empty[2 * t + qb], ((it >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[2 * t + qb], TILE_BYTES);
+          tma_load_3d(sQ + (2 * t + qb) * TILE_BYTES, &tmQ, &q_full[2 * t + qb], q_col0 + head * 64, q0 + t * 128, b);
+        }
+        for (int j = 0; j < T; ++j) {
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+          tma_load_3d(sK + st * TILE_BYTES, &tmK, &k_full[st], k_col0 + head * 64, j * 128, kvb);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+          tma_load_3d(sV + st * TILE_BYTES, &tmV, &v_full[st], v_col0 + head * 64, j * 128, kvb);
+          if (++st == KV_STAGES) { st = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -111,158 +159,201 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
-      const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ));
-      const uint64_t pdesc0 = make_smem_desc_sw128(smem_u32(sP));
-      const uint64_t pdesc1 = make_smem_desc_sw128(smem_u32(sP + TILE_BYTES));
-      mbar_wait(q_full, 0);
-      // S(0)
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      {
-        const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(&k_empty[0]);
-        umma_commit(s_full);
-      }
-      for (int j = 0; j < T; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        // O_j = P_j V_j
-        mbar_wait(p_full, j & 1);
-        mbar_wait(&v_full[st], ph);
+      const int total = my_items * T;  // key-tile steps of this CTA; step n = it * T + j
+      // state of the NEXT S to issue (same for both groups; advanced after group B)
+      int s_it = 0, s_j = 0, s_st = 0;
+      uint32_t s_ph = 0;
+      auto issue_s = [&](int t) {
+        const int qi = 2 * t + (s_it & 1);
+        if (s_j == 0) mbar_wait(&q_full[qi], (s_it >> 1) & 1);
+        mbar_wait(&k_full[s_st], s_ph);
         tc_fence_after();
-        const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + st * TILE_BYTES));
+        const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + qi * TILE_BYTES));
+        const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + s_st * TILE_BYTES));
+        const uint32_t d = tmem_base + t * 128;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
-          // V advances 16 keys = 16 rows x 128 B = 2048 B per step
-          umma_bf16(tmem_O, pd, vdesc + (2048 >> 4) * k, idesc_o, k != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(d, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        if (t == 1) umma_commit(&k_empty[s_st]);      // both query tiles have read this K tile
+        if (s_j == T - 1) umma_commit(&q_empty[qi]);  // last read of this item's Q_t
+        umma_commit(&s_full[t]);
+        if (t == 1) {
+          if (++s_st == KV_STAGES) { s_st = 0; s_ph ^= 1; }
+          if (++s_j == T) { s_j = 0; ++s_it; }
         }
-        umma_commit(&v_empty[st]);
-        umma_commit(o_full);
-        // S(j+1) may start as soon as S(j) has been consumed (= p_full(j))
-        if (j + 1 < T) {
-          const int st1 = (j + 1) & 1;
-          const uint32_t ph1 = ((j + 1) >> 1) & 1;
-          mbar_wait(&k_full[st1], ph1);
+      };
+      if (total > 0) {
+        issue_s(0);
+        issue_s(1);
+      }
+      int v_st = 0, j = 0;
+      uint32_t v_ph = 0;
+      for (int n = 0; n < total; ++n) {
+        // S_t(n+1) as soon as group t holds S_t(n) in registers
+        if (n + 1 < total) {
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&s_free[t], n & 1);
+            issue_s(t);
+          }
+        }
+        // O_t (+)= P_t(n) V(n) as soon as group t has written P_t(n)
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_full[t], n & 1);
+          if (t == 0) mbar_wait(&v_full[v_st], v_ph);
           tc_fence_after();
-          const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + st1 * TILE_BYTES));
+          const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + v_st * TILE_BYTES));
+          const uint64_t pdesc0 = make_smem_desc_sw128(smem_u32(sP + t * 2 * TILE_BYTES));
+          const uint64_t pdesc1 = make_smem_desc_sw128(smem_u32(sP + t * 2 * TILE_BYTES + TILE_BYTES));
+          const uint32_t d = tmem_base + 256 + t * 64;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(&k_empty[st1]);
-          umma_commit(s_full);
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
+            // V advances 16 keys = 16 rows x 128 B = 2048 B per step; first key tile of an item overwrites O
+            umma_bf16(d, pd, vdesc + (2048 >> 4) * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          }
+          if (t == 1) umma_commit(&v_empty[v_st]);
+          umma_commit(&o_full[t]);
         }
+        if (++v_st == KV_STAGES) { v_st = 0; v_ph ^= 1; }
+        if (++j == T) j = 0;
       }
     }
+  }
   } else {
-    // ===================== softmax warps (one query row per thread) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
+    // ===================== softmax warpgroups: one thread per query row =====================
+    const int grp = (warp - 4) >> 2;  // 0: query tile A, 1: query tile B of each item
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    float m = -INFINITY, l = 0.f;
-    float o_acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
-    uint8_t* prow = sP + r * 128;
     const int rx = r & 7;
+    const uint32_t tS = tmem_base + lane_addr + grp * 128;       // this group's S buffer
+    const uint32_t tO = tmem_base + lane_addr + 256 + grp * 64;  // this group's O accumulator
+    uint8_t* prow = sP + grp * 2 * TILE_BYTES + r * 128;         // this group's P buffer, row r
+    int n = 0;  // key-tile step counter (barrier parities)
 
-    for (int j = 0; j < T; ++j) {
-      const int nvalid = p.nk - j * 128;  // >= 1
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      // ---- pass 1: row max ----
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t s[32];
-        tmem_ld32(tmem_S + lane_addr + c, s);
-        tmem_ld_wait();
-        if (c + 32 <= nvalid) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i < nvalid) mx = fmaxf(mx, __uint_as_float(s[i]));
-        }
-      }
-      const float m_new = fmaxf(m, mx * p.scale_log2);
-      const float alpha = ex2_approx(m - m_new);  // first tile: exp2(-inf) = 0
-      // ---- fold O(j-1) and rescale ----
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
+
+    for (int it = 0; it < my_items; ++it) {
+      int q0, head, b, kvb;
+      decode(static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x), q0, head, b, kvb);
+      float m_used = -INFINITY;  // maximum the exponentials of this row are currently relative to (log2 domain)
+      float l = 0.f;
+
+      for (int j = 0; j < T; ++j, ++n) {
+        const int nvalid = p.nk - j * 128;  // >= 1
+        mbar_wait(&s_full[grp], n & 1);
         tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 64; c += 32) {
-          uint32_t o[32];
-          tmem_ld32(tmem_O + lane_addr + c, o);
+        // ---- the whole score row into registers; release the S buffer for the next Q K^T ----
+        uint32_t s[128];
+        {
+          uint32_t (&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+          uint32_t (&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+          uint32_t (&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+          uint32_t (&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+          tmem_ld32(tS, s0);
+          tmem_ld32(tS + 32, s1);
+          tmem_ld32(tS + 64, s2);
+          tmem_ld32(tS + 96, s3);
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c + i] = (o_acc[c + i] + __uint_as_float(o[i])) * alpha;
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[grp]);
+        if (nvalid < 128) {  // ragged last key tile: masked scores contribute exp2(-inf) = 0
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= nvalid) s[i] = 0xff800000u;
+        }
+        // ---- row maximum (4 independent chains) ----
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+        }
+        const float m_true = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+        // lazy rescaling: keep the old reference maximum unless the row maximum grew by more than 2^8
+        const bool raise = m_true > m_used + kRescaleThreshold;  // always true on the first tile (m_used = -inf)
+        const float m_new = raise ? m_true : m_used;
+        const float factor = raise ? ex2_approx(m_used - m_new) : 1.0f;  // first tile: exp2(-inf) = 0
+        l *= factor;
+        m_used = m_new;
+        // the previous P V of this group must be complete before P is overwritten (and before O is rescaled)
+        if (j > 0) {
+          mbar_wait(&o_full[grp], (n - 1) & 1);
+          if (__any_sync(0xffffffffu, raise)) {
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+              uint32_t o[32];
+              tmem_ld32(tO + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+              tmem_st32(tO + c, o);
+            }
+            tmem_st_wait();
+          }
+        }
+        if (j == 0 && it > 0) {
+          // the previous item's output tile was staged in this P buffer: its TMA store must have read it
+          if (warp == 4 + 4 * grp && lane == 0) tma_store_wait_read();
+          named_bar_sync(1 + grp, 128);
+        }
+        // ---- P = exp2(S*c - m_used) -> bf16, 128B-swizzled K-major tile in this group's P buffer ----
+        float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {  // 16-byte chunks of 8 keys
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(s[8 * c + i]), p.scale_log2, -m_used));
+          rs0 += e[0] + e[4];
+          rs1 += e[1] + e[5];
+          rs2 += e[2] + e[6];
+          rs3 += e[3] + e[7];
+          uint4 q;
+          q.x = pack_bf16x2(e[0], e[1]);
+          q.y = pack_bf16x2(e[2], e[3]);
+          q.z = pack_bf16x2(e[4], e[5]);
+          q.w = pack_bf16x2(e[6], e[7]);
+          *reinterpret_cast<uint4*>(prow + (c >> 3) * TILE_BYTES + (((c & 7) ^ rx) << 4)) = q;
+        }
+        l += (rs0 + rs1) + (rs2 + rs3);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[grp]);
       }
-      // ---- pass 2: P = exp2(S*c - m_new), write bf16 to swizzled smem ----
-      float rowsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t s[32];
-        tmem_ld32(tmem_S + lane_addr + c, s);
+      // ---- item epilogue: O / l -> bf16 -> 128B-swizzled smem tile (the idle P buffer) -> one TMA store ----
+      mbar_wait(&o_full[grp], (n - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / l;
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t o[32];
+        tmem_ld32(tO + c, o);
         tmem_ld_wait();
-        float pv[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_new));
-          if (c + i >= nvalid) e = 0.f;
-          pv[i] = e;
-          rowsum += e;
-        }
-        uint8_t* sub = prow + (c >> 6) * TILE_BYTES;
-        const int chunk0 = (c & 63) >> 3;  // 16-byte chunk index inside the 128-byte row
 #pragma unroll
         for (int jc = 0; jc < 4; ++jc) {
           uint4 q;
-          q.x = pack_bf16x2(pv[8 * jc + 0], pv[8 * jc + 1]);
-          q.y = pack_bf16x2(pv[8 * jc + 2], pv[8 * jc + 3]);
-          q.z = pack_bf16x2(pv[8 * jc + 4], pv[8 * jc + 5]);
-          q.w = pack_bf16x2(pv[8 * jc + 6], pv[8 * jc + 7]);
-          *reinterpret_cast<uint4*>(sub + (((chunk0 + jc) ^ rx) << 4)) = q;
+          q.x = pack_bf16x2(__uint_as_float(o[8 * jc + 0]) * inv_l, __uint_as_float(o[8 * jc + 1]) * inv_l);
+          q.y = pack_bf16x2(__uint_as_float(o[8 * jc + 2]) * inv_l, __uint_as_float(o[8 * jc + 3]) * inv_l);
+          q.z = pack_bf16x2(__uint_as_float(o[8 * jc + 4]) * inv_l, __uint_as_float(o[8 * jc + 5]) * inv_l);
+          q.w = pack_bf16x2(__uint_as_float(o[8 * jc + 6]) * inv_l, __uint_as_float(o[8 * jc + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(prow + ((((c >> 3) + jc) ^ rx) << 4)) = q;
         }
       }
-      l = l * alpha + rowsum;
-      m = m_new;
+      tc_fence_before();  // the next item's first P V overwrites O only after p_full, i.e. after these loads
       fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-    }
-    // ---- last O tile, normalise, store ----
-    mbar_wait(o_full, (T - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l;
-    const int qrow = q0 + r;
-    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.nq + qrow) * p.ldo + head * 64;
-#pragma unroll
-    for (int c = 0; c < 64; c += 32) {
-      uint32_t o[32];
-      tmem_ld32(tmem_O + lane_addr + c, o);
-      tmem_ld_wait();
-      if (qrow < p.nq) {
-#pragma unroll
-        for (int jc = 0; jc < 4; ++jc) {
-          uint4 q;
-          q.x = pack_bf16x2((o_acc[c + 8 * jc + 0] + __uint_as_float(o[8 * jc + 0])) * inv_l,
-                            (o_acc[c + 8 * jc + 1] + __uint_as_float(o[8 * jc + 1])) * inv_l);
-          q.y = pack_bf16x2((o_acc[c + 8 * jc + 2] + __uint_as_float(o[8 * jc + 2])) * inv_l,
-                            (o_acc[c + 8 * jc + 3] + __uint_as_float(o[8 * jc + 3])) * inv_l);
-          q.z = pack_bf16x2((o_acc[c + 8 * jc + 4] + __uint_as_float(o[8 * jc + 4])) * inv_l,
-                            (o_acc[c + 8 * jc + 5] + __uint_as_float(o[8 * jc + 5])) * inv_l);
-          q.w = pack_bf16x2((o_acc[c + 8 * jc + 6] + __uint_as_float(o[8 * jc + 6])) * inv_l,
-                            (o_acc[c + 8 * jc + 7] + __uint_as_float(o[8 * jc + 7])) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c + 8 * jc) = q;
-        }
+      named_bar_sync(1 + grp, 128);
+      if (warp == 4 + 4 * grp && lane == 0) {
+        // rows >= nq (ragged last tile, or a dead second tile) are clipped by the TMA unit
+        tma_store_3d(&tmO, sP + grp * 2 * TILE_BYTES, head * 64, q0 + grp * 128, b);
+        tma_store_commit();
       }
     }
+    if (warp == 4 + 4 * grp && lane == 0) tma_store_wait_all();
     tc_fence_before();
   }
 
@@ -270,7 +361,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -297,6 +388,8 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   if (make_qkv_map(&tmQ, a.q, a.ldq, a.nq, a.batch)) return 1;
   if (make_qkv_map(&tmK, a.k, a.ldk, a.nk, a.batch)) return 1;
   if (make_qkv_map(&tmV, a.v, a.ldv, a.nk, a.batch)) return 1;
+  CUtensorMap tmO;
+  if (make_qkv_map(&tmO, a.out, a.ldo, a.nq, a.batch)) return 1;
   AttnParams p;
   p.nq = a.nq;
   p.nk = a.nk;
@@ -305,8 +398,11 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.out = a.out;
   p.ldo = a.ldo;
-  dim3 grid((a.nq + 127) / 128, a.heads, a.batch);
-  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tmQ, tmK, tmV, p, a.q_col0, a.k_col0, a.v_col0);
+  p.heads = a.heads;
+  p.qpairs = (a.nq + 255) / 256;
+  p.nitems = p.qpairs * a.heads * a.batch;
+  const int grid = p.nitems < num_sms() ? p.nitems : num_sms();
+  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tmQ, tmK, tmV, tmO, p, a.q_col0, a.k_col0, a.v_col0);
   STA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
