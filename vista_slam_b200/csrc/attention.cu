@@ -109,6 +109,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+  pdl_wait();
+  pdl_launch_dependents();
 
 
   auto decode = [&](int w, int& q0, int& head, int& b, int& kvb) {
@@ -402,8 +404,8 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   p.qpairs = (a.nq + 255) / 256;
   p.nitems = p.qpairs * a.heads * a.batch;
   const int grid = p.nitems < num_sms() ? p.nitems : num_sms();
-  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tmQ, tmK, tmV, tmO, p, a.q_col0, a.k_col0, a.v_col0);
-  STA_CHECK_CUDA(cudaGetLastError());
+  STA_CHECK_CUDA(launch_pdl(attention_fwd_kernel, dim3(grid), dim3(ATT_THREADS), ATT_SMEM, stream, 1, tmQ, tmK, tmV, tmO, p,
+                            a.q_col0, a.k_col0, a.v_col0));
   return 0;
 }
 

@@ -22,6 +22,14 @@ __device__ __forceinline__ void device_fatal(const char* what) {
   __trap();
 }
 
+// Programmatic dependent launch: every kernel of the forward pass is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs may start (barrier init, TMEM allocation,
+// descriptor prefetch) while the previous kernel drains.  pdl_wait() blocks until the previous kernel has
+// completed and flushed its memory -- it must precede every global-memory access; pdl_launch_dependents()
+// lets the next kernel begin its own prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

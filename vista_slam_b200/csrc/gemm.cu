@@ -21,19 +21,7 @@ static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   const int max_items = num_sms() / CG;
   const int items = num_tiles < max_items ? num_tiles : max_items;
   if (items < 1) return 0;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(items * CG);
-  cfg.blockDim = dim3(Cfg::THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  STA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  STA_CHECK_CUDA(launch_pdl(kern, dim3(items * CG), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, CG, tmA, tmB, p));
   return 0;
 }
 

@@ -433,6 +433,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();               // previous kernel's outputs (A operand, residuals) are complete and visible
+  pdl_launch_dependents();  // the next kernel may start its prologue
 
   if (warp == 0) {
     // ===================== TMA producer (one per CTA) =====================

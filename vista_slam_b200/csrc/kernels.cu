@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int rows, float eps, const float* __restrict__ g1,
                  const float* __restrict__ b1, __nv_bfloat16* __restrict__ out1, const float* __restrict__ g2,
                  const float* __restrict__ b2, __nv_bfloat16* __restrict__ out2, int drop_first_of) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int V = C / 128;  // float4 per lane
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -86,9 +88,11 @@ int launch_layernorm(const float* x, int rows, int C, float eps, const float* g1
   if (rows <= 0) return 0;
   const int grid = (rows + 7) / 8;
   if (C == 1024)
-    layernorm_kernel<1024><<<grid, 256, 0, stream>>>(x, rows, eps, g1, b1, out1, g2, b2, out2, drop_first_of);
+    STA_CHECK_CUDA(launch_pdl(layernorm_kernel<1024>, dim3(grid), dim3(256), 0, stream, 1, x, rows, eps, g1, b1, out1, g2, b2, out2,
+                              drop_first_of));
   else if (C == 768)
-    layernorm_kernel<768><<<grid, 256, 0, stream>>>(x, rows, eps, g1, b1, out1, g2, b2, out2, drop_first_of);
+    STA_CHECK_CUDA(launch_pdl(layernorm_kernel<768>, dim3(grid), dim3(256), 0, stream, 1, x, rows, eps, g1, b1, out1, g2, b2, out2,
+                              drop_first_of));
   else {
     set_last_error("layernorm: C must be 768 or 1024");
     return 2;
@@ -105,6 +109,8 @@ int launch_layernorm(const float* x, int rows, int C, float eps, const float* g1
 template <typename T>
 __global__ void __launch_bounds__(256)
 patch_im2col_kernel(const T* __restrict__ img, int B, int H, int W, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int h = H / 16, w = W / 16;
   const long long total = static_cast<long long>(B) * h * w * 96;  // 768 / 8 chunks per patch
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -134,9 +140,11 @@ int launch_patch_im2col(const void* img, int img_is_bf16, int B, int H, int W, b
   const long long total = static_cast<long long>(B) * (H / 16) * (W / 16) * 96;
   const int grid = static_cast<int>((total + 255) / 256);
   if (img_is_bf16)
-    patch_im2col_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(img), B, H, W, out);
+    STA_CHECK_CUDA(launch_pdl(patch_im2col_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, 1,
+                              static_cast<const __nv_bfloat16*>(img), B, H, W, out));
   else
-    patch_im2col_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(img), B, H, W, out);
+    STA_CHECK_CUDA(launch_pdl(patch_im2col_kernel<float>, dim3(grid), dim3(256), 0, stream, 1, static_cast<const float*>(img), B, H, W,
+                              out));
   STA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -146,6 +154,8 @@ int launch_patch_im2col(const void* img, int img_is_bf16, int B, int H, int W, b
 // token sits at (-1, -1), sta_model.py:214-219.
 // ---------------------------------------------------------------------------
 __global__ void make_positions_kernel(int* pos, int B, int h, int w, int with_pose) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int per = h * w + (with_pose ? 1 : 0);
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(B) * per) return;
@@ -162,7 +172,8 @@ __global__ void make_positions_kernel(int* pos, int B, int h, int w, int with_po
 }
 int launch_make_positions(int* pos, int B, int h, int w, int with_pose_token, cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * (h * w + (with_pose_token ? 1 : 0));
-  make_positions_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(pos, B, h, w, with_pose_token);
+  STA_CHECK_CUDA(launch_pdl(make_positions_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, stream, 1, pos, B, h, w,
+                            with_pose_token));
   STA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -185,6 +196,8 @@ int launch_pos_from_int64(const long long* pos64, int rows, int* pos32, cudaStre
 __global__ void __launch_bounds__(256)
 cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long rows, int C,
                      int drop_first_of) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int cpr = C / 8;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= rows * cpr) return;
@@ -210,7 +223,8 @@ int launch_cast_f32_bf16(const float* in, bf16* out, long long rows, int C, int 
   STA_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
   const long long total = rows * (C / 8);
   if (total == 0) return 0;
-  cast_f32_bf16_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(in, out, rows, C, drop_first_of);
+  STA_CHECK_CUDA(launch_pdl(cast_f32_bf16_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, stream, 1, in, out, rows,
+                            C, drop_first_of));
   STA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -218,6 +232,8 @@ int launch_cast_f32_bf16(const float* in, bf16* out, long long rows, int C, int 
 // x[s, 0, :] = init_pose_token  (sta_model.py:206-212)
 __global__ void fill_pose_token_kernel(float* x, const float* __restrict__ tok, int samples, long long sample_stride,
                                        int C) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(samples) * C) return;
   const int s = static_cast<int>(idx / C);
@@ -227,13 +243,15 @@ __global__ void fill_pose_token_kernel(float* x, const float* __restrict__ tok, 
 int launch_fill_pose_token(float* x, const float* tok, int samples, int tokens_per_sample, int C,
                            cudaStream_t stream) {
   const long long total = static_cast<long long>(samples) * C;
-  fill_pose_token_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(
-      x, tok, samples, static_cast<long long>(tokens_per_sample) * C, C);
+  STA_CHECK_CUDA(launch_pdl(fill_pose_token_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, stream, 1, x, tok,
+                            samples, static_cast<long long>(tokens_per_sample) * C, C));
   STA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 __global__ void copy_f32_kernel(const float4* __restrict__ in, float4* __restrict__ out, long long n4) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx < n4) out[idx] = in[idx];
 }
@@ -241,8 +259,8 @@ int launch_copy_f32(const float* in, float* out, long long n, cudaStream_t strea
   STA_REQUIRE(n % 4 == 0, "copy length must be a multiple of 4 floats");
   const long long n4 = n / 4;
   if (n4 == 0) return 0;
-  copy_f32_kernel<<<static_cast<int>((n4 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(in),
-                                                                           reinterpret_cast<float4*>(out), n4);
+  STA_CHECK_CUDA(launch_pdl(copy_f32_kernel, dim3(static_cast<int>((n4 + 255) / 256)), dim3(256), 0, stream, 1,
+                            reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), n4));
   STA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -256,6 +274,8 @@ int launch_copy_f32(const float* in, float* out, long long n, cudaStream_t strea
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int nimg, int H, int W, int C,
                   int OH, int OW) {
+  pdl_wait();
+  pdl_launch_dependents();
   // the interpolation grid is always the full 2H x 2W one; (OH, OW) <= (2H, 2W) only crops the output
   const int FH = 2 * H, FW = 2 * W;
   const int cpp = C / 8;
@@ -297,7 +317,8 @@ int launch_upsample2x(const bf16* in, bf16* out, int nimg, int H, int W, int C, 
   STA_REQUIRE(OH <= 2 * H && OW <= 2 * W && OH > 0 && OW > 0, "output crop must fit inside the 2x grid");
   const long long total = static_cast<long long>(nimg) * OH * OW * (C / 8);
   if (total == 0) return 0;
-  upsample2x_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(in, out, nimg, H, W, C, OH, OW);
+  STA_CHECK_CUDA(launch_pdl(upsample2x_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, stream, 1, in, out, nimg, H,
+                            W, C, OH, OW));
   STA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -309,6 +330,8 @@ int launch_upsample2x(const bf16* in, bf16* out, int nimg, int H, int W, int C, 
 __global__ void __launch_bounds__(256)
 im2col_3x3_s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int nimg, int H, int W,
                      int C) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int OH = (H + 1) / 2, OW = (W + 1) / 2;  // floor((H + 2 - 3) / 2) + 1
   const int cpp = C / 8;
   const long long total = static_cast<long long>(nimg) * OH * OW * 9 * cpp;
@@ -332,7 +355,8 @@ int launch_im2col_3x3_s2(const bf16* in, bf16* out, int nimg, int H, int W, int 
   STA_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
   const long long total = static_cast<long long>(nimg) * ((H + 1) / 2) * ((W + 1) / 2) * 9 * (C / 8);
   if (total == 0) return 0;
-  im2col_3x3_s2_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(in, out, nimg, H, W, C);
+  STA_CHECK_CUDA(launch_pdl(im2col_3x3_s2_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, stream, 1, in, out, nimg,
+                            H, W, C));
   STA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -356,19 +380,37 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
   return t;
 }
 
-// y[o] = act(W[o,:] . x + b[o]); one warp per output row, coalesced weight reads.
+// y[o] = act(W[o,:] . x + b[o]).  Each warp produces 4 output rows at a time with 128-bit weight loads and
+// fully unrolled (independent) loads, so ~24 L2 requests per lane are in flight instead of one.
+template <int IN_DIM>
 __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const float* __restrict__ b,
-                                            const float* x_s, float* y_s, int in_dim, int out_dim, int relu) {
+                                            const float* x_s, float* y_s, int out_dim, int relu) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int o = warp; o < out_dim; o += 8) {
-    const float* wr = W + static_cast<long long>(o) * in_dim;
-    float acc = 0.f;
-    for (int i = lane; i < in_dim; i += 32) acc = fmaf(__ldg(wr + i), x_s[i], acc);
+  constexpr int IT = IN_DIM / 128;  // float4 per lane per row
+  float4 xv[IT];
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) {
-      acc += b[o];
-      y_s[o] = relu ? fmaxf(acc, 0.f) : acc;
+  for (int k = 0; k < IT; ++k) xv[k] = *reinterpret_cast<const float4*>(x_s + 4 * (lane + 32 * k));
+  for (int o = warp * 4; o < out_dim; o += 32) {
+    float4 wv[4][IT];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int k = 0; k < IT; ++k)
+        wv[r][k] = __ldg(reinterpret_cast<const float4*>(W + static_cast<long long>(o + r) * IN_DIM) + lane + 32 * k);
+    float acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < IT; ++k)
+        a += wv[r][k].x * xv[k].x + wv[r][k].y * xv[k].y + wv[r][k].z * xv[k].z + wv[r][k].w * xv[k].w;
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+      acc[r] = a;
+    }
+    if (lane < 4) {
+      float v = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + b[o + lane];
+      y_s[o + lane] = relu ? fmaxf(v, 0.f) : v;
     }
   }
   __syncthreads();
@@ -457,8 +499,10 @@ __device__ void svd_orthogonalize_3x3(const float* A, float* R) {
 __global__ void __launch_bounds__(256)
 pose_head_kernel(const float* __restrict__ x, long long sample_stride, int apply_ln, float eps, PoseHeadWeights w,
                  float* __restrict__ pose44, float* __restrict__ conf) {
-  __shared__ float buf0[768];
-  __shared__ float buf1[512];
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ __align__(16) float buf0[768];
+  __shared__ __align__(16) float buf1[512];
   __shared__ float red[8];
   __shared__ float outv[16];
   const int s = blockIdx.x;
@@ -481,9 +525,9 @@ pose_head_kernel(const float* __restrict__ x, long long sample_stride, int apply
 #pragma unroll
   for (int i = 0; i < 3; ++i) buf0[threadIdx.x + 256 * i] = v[i];
   __syncthreads();
-  dense_layer(w.w0, w.b0, buf0, buf1, 768, 512, 1);
-  dense_layer(w.w1, w.b1, buf1, buf0, 512, 512, 1);
-  dense_layer(w.w2, w.b2, buf0, buf1, 512, 512, 1);
+  dense_layer<768>(w.w0, w.b0, buf0, buf1, 512, 1);
+  dense_layer<512>(w.w1, w.b1, buf1, buf0, 512, 1);
+  dense_layer<512>(w.w2, w.b2, buf0, buf1, 512, 1);
   // 13 small outputs: t(3), rot(9), conf(1)
   {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -531,7 +575,8 @@ pose_head_kernel(const float* __restrict__ x, long long sample_stride, int apply
 int launch_pose_head(const float* x, long long sample_stride, int samples, int apply_ln, float eps,
                      const PoseHeadWeights& w, float* pose44, float* conf, cudaStream_t stream) {
   if (samples <= 0) return 0;
-  pose_head_kernel<<<samples, 256, 0, stream>>>(x, sample_stride, apply_ln, eps, w, pose44, conf);
+  STA_CHECK_CUDA(launch_pdl(pose_head_kernel, dim3(samples), dim3(256), 0, stream, 1, x, sample_stride, apply_ln, eps, w, pose44,
+                            conf));
   STA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
