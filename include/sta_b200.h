@@ -138,10 +138,12 @@ typedef struct StaGemmDesc {
 int sta_op_gemm(const StaGemmDesc* d, void* stream);
 
 /* softmax(q k^T * scale) v, head_dim 64.  q/k/v: [batch][n*][ld*] bf16 with head h at columns
- * *_col0 + 64*h; out: [batch][nq][ldo] bf16.  kv sample for query sample b is (b + kv_batch_shift) % batch. */
+ * *_col0 + 64*h; out: [batch][nq][ldo] bf16.  kv sample for query sample b is (b + kv_batch_shift) % batch.
+ * split_first_row != 0: query row 0 (the decoder's pose token) is computed by a small SIMT kernel and the
+ * tensor-core kernel tiles rows [1, nq) -- same result, avoids a 128-row tile for one row when nq = 128k + 1. */
 int sta_op_attention(const void* q, int64_t ldq, int q_col0, const void* k, int64_t ldk, int k_col0, const void* v,
                      int64_t ldv, int v_col0, void* out, int64_t ldo, int batch, int heads, int nq, int nk,
-                     int kv_batch_shift, float scale, void* stream);
+                     int kv_batch_shift, float scale, int split_first_row, void* stream);
 
 int sta_op_layernorm(const float* x, int rows, int C, float eps, const float* g1, const float* b1, void* out1_bf16,
                      const float* g2, const float* b2, void* out2_bf16, int drop_first_of, void* stream);

@@ -42,7 +42,7 @@ def test_implicit_gemm_conv_and_head(capsys):
 
 
 def test_attention_self_and_cross(capsys):
-    assert len(_collect(bu.group_attention, capsys)) == 5
+    assert len(_collect(bu.group_attention, capsys)) == 10
 
 
 def test_bandwidth_kernels(capsys):
@@ -72,7 +72,7 @@ def test_attention_uniform_values_property():
         qkv[..., 2 * C:] = 0.5
         out = torch.zeros(2, n, C, device=dev, dtype=torch.bfloat16)
         check(lib().sta_op_attention(ptr(qkv), 3 * C, 0, ptr(qkv), 3 * C, C, ptr(qkv), 3 * C, 2 * C, ptr(out), C, 2, 2, n, n, 0,
-                                     0.125, cur_stream()))
+                                     0.125, 0, cur_stream()))
         torch.cuda.synchronize()
         assert torch.allclose(out.float(), torch.full_like(out, 0.5).float(), atol=4e-3), n
 

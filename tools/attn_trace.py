@@ -9,7 +9,7 @@ C = heads * 64
 qkv = torch.randn(batch, n, 3 * C, device="cuda").bfloat16()
 out = torch.zeros(batch, n, C, device="cuda", dtype=torch.bfloat16)
 for _ in range(3):
-    check(L.sta_op_attention(ptr(qkv), 3 * C, 0, ptr(qkv), 3 * C, C, ptr(qkv), 3 * C, 2 * C, ptr(out), C, batch, heads, n, n, 0, 0.125, cur_stream()))
+    check(L.sta_op_attention(ptr(qkv), 3 * C, 0, ptr(qkv), 3 * C, C, ptr(qkv), 3 * C, 2 * C, ptr(out), C, batch, heads, n, n, 0, 0.125, 0, cur_stream()))
 torch.cuda.synchronize()
 b = buf.cpu().tolist()
 t0 = min(x for x in b if x > 0)

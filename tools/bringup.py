@@ -203,19 +203,21 @@ def group_attention():
     torch.manual_seed(3)
     dev = "cuda"
     L = lib()
-    for (batch, heads, n, shift) in [(2, 3, 128, 0), (2, 3, 196, 0), (2, 12, 769, 0), (4, 12, 769, 2), (3, 16, 768, 0)]:
+    for (batch, heads, n, shift, split) in [(2, 3, 128, 0, 0), (2, 3, 196, 0, 0), (2, 12, 769, 0, 0), (4, 12, 769, 2, 0),
+                                            (3, 16, 768, 0, 0), (4, 12, 769, 2, 1), (2, 12, 197, 0, 1), (2, 3, 130, 0, 1),
+                                            (2, 3, 257, 1, 1), (3, 2, 1, 0, 1)]:
         C = heads * 64
         qkv = torch.randn(batch, n, 3 * C, device=dev).bfloat16()
         out = torch.zeros(batch, n, C, device=dev, dtype=torch.bfloat16)
         check(L.sta_op_attention(ptr(qkv), 3 * C, 0, ptr(qkv), 3 * C, C, ptr(qkv), 3 * C, 2 * C, ptr(out), C, batch,
-                                 heads, n, n, shift, 0.125, cur_stream()), "attention")
+                                 heads, n, n, shift, 0.125, split, cur_stream()), "attention")
         torch.cuda.synchronize()
         q, k, v = [qkv[..., i * C:(i + 1) * C].float().view(batch, n, heads, 64).transpose(1, 2) for i in range(3)]
         if shift:
             idx = [(b + shift) % batch for b in range(batch)]
             k, v = k[idx], v[idx]
         ref = F.scaled_dot_product_attention(q, k, v, scale=0.125).transpose(1, 2).reshape(batch, n, C)
-        report("attention b%d h%d n%d shift%d" % (batch, heads, n, shift), out, ref, 2e-2)
+        report("attention b%d h%d n%d shift%d split%d" % (batch, heads, n, shift, split), out, ref, 2e-2)
 
 
 def group_misc():
@@ -308,14 +310,14 @@ def group_perf():
         print("gemm M%d N%d K%d epi%d: %.3f ms = %.0f TFLOP/s   (torch.matmul %.3f ms = %.0f TFLOP/s)" %
               (M, N, K, epi, ms, 2.0 * M * N * K / ms / 1e9, ms_t, 2.0 * M * N * K / ms_t / 1e9), flush=True)
     L = lib()
-    for (batch, heads, n) in [(32, 16, 768), (32, 12, 769)]:
+    for (batch, heads, n, split) in [(32, 16, 768, 0), (32, 12, 769, 0), (32, 12, 769, 1)]:
         C = heads * 64
         qkv = torch.randn(batch, n, 3 * C, device=dev).bfloat16()
         out = torch.zeros(batch, n, C, device=dev, dtype=torch.bfloat16)
         ms = timeit(lambda: check(L.sta_op_attention(ptr(qkv), 3 * C, 0, ptr(qkv), 3 * C, C, ptr(qkv), 3 * C, 2 * C,
-                                                     ptr(out), C, batch, heads, n, n, 0, 0.125, cur_stream())))
+                                                     ptr(out), C, batch, heads, n, n, 0, 0.125, split, cur_stream())))
         fl = 4.0 * batch * heads * n * n * 64
-        print("attention b%d h%d n%d: %.3f ms = %.0f TFLOP/s" % (batch, heads, n, ms, fl / ms / 1e9), flush=True)
+        print("attention b%d h%d n%d split%d: %.3f ms = %.0f TFLOP/s" % (batch, heads, n, split, ms, fl / ms / 1e9), flush=True)
 
 
 def main():

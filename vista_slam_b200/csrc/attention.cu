@@ -49,6 +49,7 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 struct AttnParams {
   int nq, nk, batch, heads, qpairs, kv_batch_shift;
   int nitems;
+  int q_row0;  // first query row handled by the tiled kernel (1 when row 0 goes to attention_row0_kernel)
   float scale_log2;
   __nv_bfloat16* out;
   long long ldo;
@@ -118,7 +119,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int rest = w / p.qpairs;
     head = rest % p.heads;
     b = rest / p.heads;
-    q0 = qp * 256;
+    q0 = p.q_row0 + qp * 256;
     kvb = (b + p.kv_batch_shift) % p.batch;
   };
   const int my_items = (p.nitems > static_cast<int>(blockIdx.x))
@@ -160,7 +161,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
+      constexpr uint32_t idesc_s16 = make_idesc_bf16(128, 16, 0, 0);  // narrow tail tile (<= 16 valid keys)
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);    // B (= V) is MN-major
+      const bool narrow_tail = (p.nk - (T - 1) * 128) <= 16;
       const int total = my_items * T;  // key-tile steps of this CTA; step n = it * T + j
       // state of the NEXT S to issue (same for both groups; advanced after group B)
       int s_it = 0, s_j = 0, s_st = 0;
@@ -173,8 +176,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + qi * TILE_BYTES));
         const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + s_st * TILE_BYTES));
         const uint32_t d = tmem_base + t * 128;
+        const uint32_t ids = (narrow_tail && s_j == T - 1) ? idesc_s16 : idesc_s;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(d, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(d, qdesc + 2 * k, kdesc + 2 * k, ids, k != 0);
         if (t == 1) umma_commit(&k_empty[s_st]);      // both query tiles have read this K tile
         if (s_j == T - 1) umma_commit(&q_empty[qi]);  // last read of this item's Q_t
         umma_commit(&s_full[t]);
@@ -206,8 +210,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint64_t pdesc0 = make_smem_desc_sw128(smem_u32(sP + t * 2 * TILE_BYTES));
           const uint64_t pdesc1 = make_smem_desc_sw128(smem_u32(sP + t * 2 * TILE_BYTES + TILE_BYTES));
           const uint32_t d = tmem_base + 256 + t * 64;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
+          const int ksteps = (narrow_tail && j == T - 1) ? 1 : 8;  // a narrow tail tile holds <= 16 keys
+          for (int k = 0; k < ksteps; ++k) {
             const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
             // V advances 16 keys = 16 rows x 128 B = 2048 B per step; first key tile of an item overwrites O
             umma_bf16(d, pd, vdesc + (2048 >> 4) * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
@@ -244,6 +248,69 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int nvalid = p.nk - j * 128;  // >= 1
         mbar_wait(&s_full[grp], n & 1);
         tc_fence_after();
+        if (nvalid <= 16 && j == T - 1) {
+          // ---- narrow tail tile: S is 128 x 16, P V uses a single 16-key step ----
+          uint32_t s16[16];
+          tmem_ld16(tS, s16);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[grp]);
+          float mxn = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (i >= nvalid) s16[i] = 0xff800000u;
+            mxn = fmaxf(mxn, __uint_as_float(s16[i]));
+          }
+          const float m_true = mxn * p.scale_log2;
+          const bool raise = m_true > m_used + kRescaleThreshold;
+          const float m_new = raise ? m_true : m_used;
+          const float factor = raise ? ex2_approx(m_used - m_new) : 1.0f;
+          l *= factor;
+          m_used = m_new;
+          if (j > 0) {
+            mbar_wait(&o_full[grp], (n - 1) & 1);
+            if (__any_sync(0xffffffffu, raise)) {
+              tc_fence_after();
+#pragma unroll
+              for (int c = 0; c < 64; c += 32) {
+                uint32_t o[32];
+                tmem_ld32(tO + c, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                tmem_st32(tO + c, o);
+              }
+              tmem_st_wait();
+            }
+          }
+          if (j == 0 && it > 0) {
+            if (warp == 4 + 4 * grp && lane == 0) tma_store_wait_read();
+            named_bar_sync(1 + grp, 128);
+          }
+          float rs = 0.f;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              e[i] = ex2_approx(fmaf(__uint_as_float(s16[8 * c + i]), p.scale_log2, -m_used));
+              rs += e[i];
+            }
+            uint4 q;
+            q.x = pack_bf16x2(e[0], e[1]);
+            q.y = pack_bf16x2(e[2], e[3]);
+            q.z = pack_bf16x2(e[4], e[5]);
+            q.w = pack_bf16x2(e[6], e[7]);
+            *reinterpret_cast<uint4*>(prow + ((c ^ rx) << 4)) = q;
+          }
+          l += rs;
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[grp]);
+          continue;
+        }
         // ---- the whole score row into registers; release the S buffer for the next Q K^T ----
         uint32_t s[128];
         {
@@ -367,6 +434,87 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------
+// Query row 0 of every (sample, head) -- the decoder's pose token -- against all nk keys.
+// One CTA (256 threads) per (head, sample): scores -> shared memory, block max / sum, then the
+// 64 output features as coalesced column sums over V.  ~1e-4 of the attention FLOPs.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attention_row0_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, int q_col0, const __nv_bfloat16* __restrict__ k,
+                      long long ldk, int k_col0, const __nv_bfloat16* __restrict__ v, long long ldv, int v_col0,
+                      __nv_bfloat16* __restrict__ out, long long ldo, int nq, int nk, int batch, int kv_batch_shift,
+                      float scale_log2) {
+  extern __shared__ float sc[];  // nk scores | 16 floats of reduction scratch | 256 partial outputs
+  float* red = sc + ((nk + 3) & ~3);
+  __shared__ float qs[64];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int kvb = (b + kv_batch_shift) % batch;
+  const int tid = threadIdx.x;
+  if (tid < 64) qs[tid] = __bfloat162float(q[static_cast<long long>(b) * nq * ldq + q_col0 + head * 64 + tid]);
+  __syncthreads();
+  // ---- scores: one key per thread per round (8 x 16-byte loads in flight per key) ----
+  const __nv_bfloat16* kb = k + static_cast<long long>(kvb) * nk * ldk + k_col0 + head * 64;
+  float mx = -INFINITY;
+  for (int j = tid; j < nk; j += 256) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kb + static_cast<long long>(j) * ldk);
+    uint4 w[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w[c] = __ldg(kr + c);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      acc += qs[8 * c + 0] * bf16_lo(w[c].x) + qs[8 * c + 1] * bf16_hi(w[c].x) + qs[8 * c + 2] * bf16_lo(w[c].y) +
+             qs[8 * c + 3] * bf16_hi(w[c].y) + qs[8 * c + 4] * bf16_lo(w[c].z) + qs[8 * c + 5] * bf16_hi(w[c].z) +
+             qs[8 * c + 6] * bf16_lo(w[c].w) + qs[8 * c + 7] * bf16_hi(w[c].w);
+    }
+    acc *= scale_log2;
+    sc[j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  float sum = 0.f;
+  for (int j = tid; j < nk; j += 256) {
+    // P is rounded to bf16 like in the tiled kernel; the row sum uses the unrounded value
+    const float e = ex2_approx(sc[j] - mx);
+    sum += e;
+    sc[j] = __bfloat162float(__float2bfloat16(e));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((tid & 31) == 0) red[8 + (tid >> 5)] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[8 + i];
+  // ---- output feature d = tid & 63; the 4 quarter-blocks take keys j = g (mod 4); 8 independent loads in flight ----
+  const int d = tid & 63, g = tid >> 6;
+  const __nv_bfloat16* vb = v + static_cast<long long>(kvb) * nk * ldv + v_col0 + head * 64 + d;
+  float o = 0.f;
+  int j = g;
+  for (; j + 28 < nk; j += 32) {
+    float vv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) vv[u] = __bfloat162float(vb[static_cast<long long>(j + 4 * u) * ldv]);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) o = fmaf(sc[j + 4 * u], vv[u], o);
+  }
+  for (; j < nk; j += 4) o = fmaf(sc[j], __bfloat162float(vb[static_cast<long long>(j) * ldv]), o);
+  float* part = red + 16;
+  part[tid] = o;
+  __syncthreads();
+  if (tid < 64)
+    out[static_cast<long long>(b) * nq * ldo + head * 64 + tid] =
+        __float2bfloat16(((part[tid] + part[tid + 64]) + (part[tid + 128] + part[tid + 192])) / sum);
+}
+
 int make_qkv_map(CUtensorMap* m, const bf16* base, long long ld, int ntok, int batch) {
   uint64_t dims[3] = {(uint64_t)ld, (uint64_t)ntok, (uint64_t)batch};
   uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)ntok};
@@ -401,8 +549,16 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   p.out = a.out;
   p.ldo = a.ldo;
   p.heads = a.heads;
-  p.qpairs = (a.nq + 255) / 256;
+  const int split = (a.split_first_row && a.nq > 1) ? 1 : 0;
+  p.q_row0 = split;
+  p.qpairs = (a.nq - split + 255) / 256;
   p.nitems = p.qpairs * a.heads * a.batch;
+  if (split) {
+    const size_t smem = (((a.nk + 3) & ~3) + 16 + 256) * sizeof(float);
+    STA_CHECK_CUDA(launch_pdl(attention_row0_kernel, dim3(a.heads, a.batch), dim3(256), smem, stream, 1, a.q, a.ldq, a.q_col0, a.k,
+                              a.ldk, a.k_col0, a.v, a.ldv, a.v_col0, a.out, a.ldo, a.nq, a.nk, a.batch, a.kv_batch_shift,
+                              p.scale_log2));
+  }
   const int grid = p.nitems < num_sms() ? p.nitems : num_sms();
   STA_CHECK_CUDA(launch_pdl(attention_fwd_kernel, dim3(grid), dim3(ATT_THREADS), ATT_SMEM, stream, 1, tmQ, tmK, tmV, tmO, p,
                             a.q_col0, a.k_col0, a.v_col0));

@@ -36,6 +36,10 @@ struct AttnLaunch {
   int batch = 0, heads = 0, nq = 0, nk = 0;
   int kv_batch_shift = 0;   // k/v sample for query sample b is (b + shift) % batch  (cross-view attention)
   float scale = 0.125f;
+  // The decoder's token count is 128*k + 1 (pose token + patches).  With split_first_row the tiled kernel
+  // handles query rows [1, nq) -- whole 128-row tiles -- and a small SIMT kernel handles query row 0 of every
+  // (sample, head), instead of paying a whole extra query tile for one row.
+  int split_first_row = 0;
 };
 int launch_attention(const AttnLaunch& a, cudaStream_t stream);
 

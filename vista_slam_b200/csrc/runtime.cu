@@ -469,7 +469,8 @@ int ln(const Ctx& c, const float* x, int rows, int C, const LNp& a, bf16* out1, 
                           drop_first_of, c.st);
 }
 int attn(const Ctx& c, const bf16* q, long long ldq, int qc, const bf16* k, long long ldk, int kc, const bf16* v,
-         long long ldv, int vc, bf16* out, long long ldo, int batch, int heads, int nq, int nk, int shift) {
+         long long ldv, int vc, bf16* out, long long ldo, int batch, int heads, int nq, int nk, int shift,
+         int split_first_row = 0) {
   AttnLaunch a;
   a.q = q; a.ldq = ldq; a.q_col0 = qc;
   a.k = k; a.ldk = ldk; a.k_col0 = kc;
@@ -477,6 +478,7 @@ int attn(const Ctx& c, const bf16* q, long long ldq, int qc, const bf16* k, long
   a.out = out; a.ldo = ldo;
   a.batch = batch; a.heads = heads; a.nq = nq; a.nk = nk;
   a.kv_batch_shift = shift;
+  a.split_first_row = split_first_row;
   a.scale = 0.125f;  // head_dim ** -0.5, sta_blocks.py:86
   c.m->launches++;
   ProfScope ps(c, PROF_ATTN, 4.0 * batch * heads * static_cast<double>(nq) * nk * 64);
@@ -623,14 +625,14 @@ int run_decoder(const Ctx& c, int B, int N, DecBufs& d, float* const* out1, floa
     RUN(ln(c, d.xd, Td, kDecDim, b.n1, d.ln1, &b.ny, d.lny));
     RUN(linear(c, EPI_ROPE, d.ln1, Td, b.qkv, d.qkv, nullptr, d.pos, 2 * kDecDim));
     RUN(attn(c, d.qkv, 3 * kDecDim, 0, d.qkv, 3 * kDecDim, kDecDim, d.qkv, 3 * kDecDim, 2 * kDecDim, d.att, kDecDim, S,
-             kDecHeads, M, M, 0));
+             kDecHeads, M, M, 0, /*split_first_row=*/0));
     RUN(linear(c, EPI_F32, d.att, Td, b.proj, d.xd, d.xd));
     // cross-attention: q from norm2(x), k/v from norm_y(partner input) -- kv sample = (s + B) % 2B
     RUN(linear(c, EPI_ROPE, d.lny, Td, b.ckv, d.kvc, nullptr, d.pos, kDecDim));
     RUN(ln(c, d.xd, Td, kDecDim, b.n2, d.ln1));
     RUN(linear(c, EPI_ROPE, d.ln1, Td, b.cq, d.qc, nullptr, d.pos, kDecDim));
     RUN(attn(c, d.qc, kDecDim, 0, d.kvc, 2 * kDecDim, 0, d.kvc, 2 * kDecDim, kDecDim, d.att, kDecDim, S, kDecHeads, M, M,
-             B));
+             B, /*split_first_row=*/0));
     RUN(linear(c, EPI_F32, d.att, Td, b.cproj, d.xd, d.xd));
     // MLP
     RUN(ln(c, d.xd, Td, kDecDim, b.n3, d.ln1));
@@ -1184,7 +1186,7 @@ int sta_op_gemm(const StaGemmDesc* d, void* stream) {
 
 int sta_op_attention(const void* q, int64_t ldq, int q_col0, const void* k, int64_t ldk, int k_col0, const void* v,
                      int64_t ldv, int v_col0, void* out, int64_t ldo, int batch, int heads, int nq, int nk,
-                     int kv_batch_shift, float scale, void* stream) {
+                     int kv_batch_shift, float scale, int split_first_row, void* stream) {
   AttnLaunch a;
   a.q = static_cast<const bf16*>(q); a.ldq = ldq; a.q_col0 = q_col0;
   a.k = static_cast<const bf16*>(k); a.ldk = ldk; a.k_col0 = k_col0;
@@ -1193,6 +1195,7 @@ int sta_op_attention(const void* q, int64_t ldq, int q_col0, const void* k, int6
   a.batch = batch; a.heads = heads; a.nq = nq; a.nk = nk;
   a.kv_batch_shift = kv_batch_shift;
   a.scale = scale;
+  a.split_first_row = split_first_row;
   return launch_attention(a, static_cast<cudaStream_t>(stream));
 }
 
