@@ -34,6 +34,17 @@ METRIC = "sta_image_pairs_per_sec"
 UNIT = "pairs/s"
 
 
+def make_config(P, world, H, W):
+    from vista_slam_b200.flops import flops_per_pair
+    return {"workload": "cfg-2: %d synthetic %dx%d bf16 pairs per GPU per step, STA forward only "
+                        "(2 enc + symmetric dec + 2 DPT + 2 pose heads per pair), random-init weights" % (P, W, H),
+            "pairs_per_gpu": P, "global_pairs": P * world, "height": H, "width": W,
+            "parallelism": "pair shard per rank, 1 NCCL weight broadcast, no data-path collective",
+            "l2_policy": "no explicit flush: per-step working set (0.88 GB weights + >2 GB activations) "
+                         "exceeds the 126 MB L2",
+            "gflop_per_pair": flops_per_pair(H, W) / 1e9}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -146,9 +157,9 @@ def run_reference_arm(args, rank, world):
         "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "cfg-2 shape: synthetic %dx%d pairs, STA forward only (2 enc + sym. dec + 2 DPT + 2 pose); "
-                               "reference CPU path = oracle port, 1 pair per step (bounded sample)" % (W, H),
-                   "pairs_per_step": 1, "height": H, "width": W},
+        "config": dict(make_config(args.pairs, args.gpus, H, W),
+                       reference_sample="reference CPU path = oracle port (PyTorch fp32, %d threads); each step is a bounded "
+                                        "sample of the workload: 1 pair of the %d-pair batch" % (cores, args.pairs)),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d timed single-pair forwards at %dx%d fp32, %d threads" % (args.steps, W, H, cores)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -251,7 +262,11 @@ def run_b200_arm(args, rank, local_rank, world):
     peak = peaks["bf16_sustained"] or peaks["bf16_burst"]
     roofline = {
         "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM 3x3 conv family)",
-        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        # DRAM bytes per launch: mean over the 4 consecutive gemm_tc_kernel launches of one ncu --set full capture
+        # (profiles/r01_ncu_gemm_full_summary.txt; read+write 142 / 278 / 104 / 136 MB, equal to the operand + output
+        # sizes of those launches, i.e. no re-reads); the family is tensor-bound, so this is context, not the bound
+        "traffic": 165.0e6, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
         "peak_source": peaks["source"] + ", sustained cuBLAS bf16 (kernel timed inside a long step)",
         "launches_per_step": int(gemm_launches), "avg_launch_ms": gemm_ms / max(1, gemm_launches),
         "algorithmic_gflop_per_launch_avg": P * gemm_flops_pair / max(1, gemm_launches) / 1e9,
@@ -273,13 +288,7 @@ def run_b200_arm(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "impl": "b200",
-            "config": {"workload": "cfg-2: %d synthetic %dx%d bf16 pairs per GPU per step, STA forward only "
-                                   "(2 enc + symmetric dec + 2 DPT + 2 pose heads per pair), random-init weights" % (P, W, H),
-                       "pairs_per_gpu": P, "global_pairs": P * world, "height": H, "width": W,
-                       "parallelism": "pair shard per rank, 1 NCCL weight broadcast, no data-path collective",
-                       "l2_policy": "no explicit flush: per-step working set (0.88 GB weights + >2 GB activations) "
-                                    "exceeds the 126 MB L2",
-                       "gflop_per_pair": flop_pair / 1e9},
+            "config": make_config(P, world, H, W),
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                                       "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "outputs_finite": ok,

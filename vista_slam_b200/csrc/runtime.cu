@@ -183,6 +183,9 @@ struct StaModel {
   size_t stage_bytes = 0;
   char* io = nullptr;      // device staging for sta_forward_pairs_host
   size_t io_bytes = 0;
+  static constexpr int kMaxHostChunks = 32;
+  cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the host entry point
+  cudaEvent_t ev_in[kMaxHostChunks] = {}, ev_done[kMaxHostChunks] = {}, ev_start = nullptr;
   int64_t launches = 0;
   int max_pairs_per_chunk = 16;
 
@@ -879,6 +882,15 @@ void sta_destroy(StaModel* m) {
   if (m->ws.base) cudaFree(m->ws.base);
   if (m->stage) cudaFree(m->stage);
   if (m->io) cudaFree(m->io);
+  if (m->s_in) {
+    cudaStreamDestroy(m->s_in);
+    cudaStreamDestroy(m->s_out);
+    for (int i = 0; i < StaModel::kMaxHostChunks; ++i) {
+      cudaEventDestroy(m->ev_in[i]);
+      cudaEventDestroy(m->ev_done[i]);
+    }
+    cudaEventDestroy(m->ev_start);
+  }
   for (auto& r : m->prof_recs) {
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
@@ -1111,6 +1123,7 @@ int sta_forward_pairs_host(StaModel* m, const void* img1_host, const void* img2_
                            float* pose_conf_out_host, void* stream) {
   RUN(check_ready(m));
   STA_REQUIRE(B > 0 && H % 16 == 0 && W % 16 == 0 && H > 0 && W > 0, "image size must be a positive multiple of 16");
+  STA_REQUIRE(H / 16 <= 1024 && W / 16 <= 1024, "token grid exceeds the RoPE table");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t esz = img_is_bf16 ? 2 : 4;
   const size_t px = static_cast<size_t>(H) * W;
@@ -1129,6 +1142,15 @@ int sta_forward_pairs_host(StaModel* m, const void* img1_host, const void* img2_
     STA_CHECK_CUDA(cudaMalloc(&m->io, need));
     m->io_bytes = need;
   }
+  if (!m->s_in) {
+    STA_CHECK_CUDA(cudaStreamCreateWithFlags(&m->s_in, cudaStreamNonBlocking));
+    STA_CHECK_CUDA(cudaStreamCreateWithFlags(&m->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < StaModel::kMaxHostChunks; ++i) {
+      STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming));
+      STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
+    }
+    STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
+  }
   char* p = m->io;
   char* d_img1 = p; p += up(img_bytes);
   char* d_img2 = p; p += up(img_bytes);
@@ -1136,13 +1158,53 @@ int sta_forward_pairs_host(StaModel* m, const void* img1_host, const void* img2_
   float* d_conf = reinterpret_cast<float*>(p); p += up(conf_bytes);
   float* d_pose = reinterpret_cast<float*>(p); p += up(pose_bytes);
   float* d_pconf = reinterpret_cast<float*>(p);
-  STA_CHECK_CUDA(cudaMemcpyAsync(d_img1, img1_host, img_bytes, cudaMemcpyHostToDevice, st));
-  STA_CHECK_CUDA(cudaMemcpyAsync(d_img2, img2_host, img_bytes, cudaMemcpyHostToDevice, st));
-  RUN(sta_forward_pairs(m, d_img1, d_img2, img_is_bf16, B, H, W, d_pts, d_conf, d_pose, d_pconf, stream));
-  STA_CHECK_CUDA(cudaMemcpyAsync(pts3d_out_host, d_pts, pts_bytes, cudaMemcpyDeviceToHost, st));
-  STA_CHECK_CUDA(cudaMemcpyAsync(conf_out_host, d_conf, conf_bytes, cudaMemcpyDeviceToHost, st));
-  STA_CHECK_CUDA(cudaMemcpyAsync(pose_out_host, d_pose, pose_bytes, cudaMemcpyDeviceToHost, st));
-  STA_CHECK_CUDA(cudaMemcpyAsync(pose_conf_out_host, d_pconf, pconf_bytes, cudaMemcpyDeviceToHost, st));
+
+  // Pipeline over chunks of pairs: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the compute
+  // of chunk c (separate copy streams, pinned host memory makes them truly asynchronous).
+  int cp = (B >= 16) ? 8 : B;
+  if (cp > m->max_pairs_per_chunk) cp = m->max_pairs_per_chunk;
+  int nchunks = (B + cp - 1) / cp;
+  if (nchunks > StaModel::kMaxHostChunks) {
+    nchunks = StaModel::kMaxHostChunks;
+    cp = (B + nchunks - 1) / nchunks;
+    STA_REQUIRE(cp <= m->max_pairs_per_chunk, "batch too large for the host entry point; split it");
+    nchunks = (B + cp - 1) / cp;
+  }
+  // the copy streams must not start before previously enqueued work on `st` that may still use the io buffers
+  STA_CHECK_CUDA(cudaEventRecord(m->ev_start, st));
+  STA_CHECK_CUDA(cudaStreamWaitEvent(m->s_in, m->ev_start, 0));
+  STA_CHECK_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_start, 0));
+  const size_t img_pair = 3 * px * esz;
+  for (int c = 0; c < nchunks; ++c) {
+    const int b0 = c * cp, nb = (B - b0 < cp) ? (B - b0) : cp;
+    STA_CHECK_CUDA(cudaMemcpyAsync(d_img1 + b0 * img_pair, static_cast<const char*>(img1_host) + b0 * img_pair,
+                                   nb * img_pair, cudaMemcpyHostToDevice, m->s_in));
+    STA_CHECK_CUDA(cudaMemcpyAsync(d_img2 + b0 * img_pair, static_cast<const char*>(img2_host) + b0 * img_pair,
+                                   nb * img_pair, cudaMemcpyHostToDevice, m->s_in));
+    STA_CHECK_CUDA(cudaEventRecord(m->ev_in[c], m->s_in));
+  }
+  Ctx cx{m, st};
+  for (int c = 0; c < nchunks; ++c) {
+    const int b0 = c * cp, nb = (B - b0 < cp) ? (B - b0) : cp;
+    STA_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_in[c], 0));
+    RUN(forward_chunk(cx, d_img1 + b0 * img_pair, d_img2 + b0 * img_pair, img_is_bf16, nb, H, W,
+                      d_pts + static_cast<size_t>(b0) * px * 3, d_conf + static_cast<size_t>(b0) * px,
+                      d_pose + static_cast<size_t>(b0) * 16, d_pconf + b0, B));
+    STA_CHECK_CUDA(cudaEventRecord(m->ev_done[c], st));
+    STA_CHECK_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_done[c], 0));
+    for (int v = 0; v < 2; ++v) {
+      const size_t o = static_cast<size_t>(v) * B + b0;
+      STA_CHECK_CUDA(cudaMemcpyAsync(pts3d_out_host + o * px * 3, d_pts + o * px * 3, nb * px * 3 * sizeof(float),
+                                     cudaMemcpyDeviceToHost, m->s_out));
+      STA_CHECK_CUDA(cudaMemcpyAsync(conf_out_host + o * px, d_conf + o * px, nb * px * sizeof(float),
+                                     cudaMemcpyDeviceToHost, m->s_out));
+      STA_CHECK_CUDA(cudaMemcpyAsync(pose_out_host + o * 16, d_pose + o * 16, nb * 16 * sizeof(float),
+                                     cudaMemcpyDeviceToHost, m->s_out));
+      STA_CHECK_CUDA(cudaMemcpyAsync(pose_conf_out_host + o, d_pconf + o, nb * sizeof(float), cudaMemcpyDeviceToHost,
+                                     m->s_out));
+    }
+  }
+  STA_CHECK_CUDA(cudaStreamSynchronize(m->s_out));
   STA_CHECK_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
