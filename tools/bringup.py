@@ -309,6 +309,28 @@ def group_perf():
         ms_t = timeit(lambda: torch.matmul(A, W.t()))
         print("gemm M%d N%d K%d epi%d: %.3f ms = %.0f TFLOP/s   (torch.matmul %.3f ms = %.0f TFLOP/s)" %
               (M, N, K, epi, ms, 2.0 * M * N * K / ms / 1e9, ms_t, 2.0 * M * N * K / ms_t / 1e9), flush=True)
+    # epilogue variants on the trunk shapes
+    from vista_slam_b200._lib import EPI_F32, EPI_ROPE
+    M = 24576
+    for (N, K, epi, name) in [(3072, 1024, EPI_ROPE, "rope (enc qkv)"), (1024, 1024, EPI_F32, "f32+resid (enc proj)"),
+                              (1024, 4096, EPI_F32, "f32+resid (enc fc2)"), (2304, 768, EPI_ROPE, "rope (dec qkv)"),
+                              (768, 768, EPI_F32, "f32+resid (dec proj)"), (3072, 768, EPI_GELU, "gelu (dec fc1)")]:
+        A = torch.randn(M, K, device=dev).bfloat16()
+        W = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+        bias = torch.randn(N, device=dev)
+        if epi == EPI_F32:
+            out = torch.zeros(M, N, device=dev)
+            d = gemm_desc(epi=epi, A=A, lda=K, W=W, ldw=K, M=M, N=N, K=K, bias=bias, out=out, ldo=N, resid=out)
+        elif epi == EPI_ROPE:
+            out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+            pos = torch.randint(0, 32, (M, 2), device=dev, dtype=torch.int32)
+            d = gemm_desc(epi=epi, A=A, lda=K, W=W, ldw=K, M=M, N=N, K=K, bias=bias, out=out, ldo=N, pos=pos,
+                          rope_cols=2 * N // 3)
+        else:
+            out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+            d = gemm_desc(epi=epi, A=A, lda=K, W=W, ldw=K, M=M, N=N, K=K, bias=bias, out=out, ldo=N)
+        ms = timeit(lambda: run_gemm(d))
+        print("gemm-epi %-22s M%d N%d K%d: %.3f ms = %.0f TFLOP/s" % (name, M, N, K, ms, 2.0 * M * N * K / ms / 1e9), flush=True)
     L = lib()
     for (batch, heads, n, split) in [(32, 16, 768, 0), (32, 12, 769, 0), (32, 12, 769, 1)]:
         C = heads * 64

@@ -9,7 +9,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsta_b200.so")
+LIB_PATH = os.environ.get("STA_B200_LIB") or os.path.join(_HERE, "csrc", "libsta_b200.so")  # env override: A/B timing of builds
 
 EPI_BF16, EPI_GELU, EPI_F32, EPI_ROPE, EPI_PIXSHUF, EPI_HEAD = range(6)
 

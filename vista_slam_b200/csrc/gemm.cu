@@ -7,11 +7,11 @@
 
 namespace sta {
 
-template <int BN, int AMODE, int EPI, int CG>
+template <int BN, int AMODE, int EPI, int CG, int EW>
 static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_tiles,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG>;
-  auto kern = gemm_tc_kernel<BN, AMODE, EPI, CG>;
+  using Cfg = GemmCfg<BN, CG, EW>;
+  auto kern = gemm_tc_kernel<BN, AMODE, EPI, CG, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     STA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
@@ -37,6 +37,10 @@ static int cta_group_mode() {
 
 int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
   GemmParams p = g.p;
+  {
+    const char* e = getenv("STA_GEMM_TRACE");
+    p.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+  }
   STA_REQUIRE(p.N % 32 == 0, "N must be a multiple of 32");
   STA_REQUIRE(g.A != nullptr && g.Wt != nullptr, "null operand");
   STA_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.Wt) & 15) == 0,
@@ -86,12 +90,28 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
   const int n_tiles = (p.N + bn - 1) / bn;
   const int num_tiles = ((m_tiles + cg - 1) / cg) * n_tiles;
 
-#define STA_GEMM_CASE(BN_, AM_, EP_)                                                   \
-  if (bn == BN_ && g.amode == AM_ && g.epi == EP_) {                                   \
-    if (cg == 2) return launch_inst<BN_, AM_, EP_, 2>(tmA, tmB, p, num_tiles, stream); \
-    return launch_inst<BN_, AM_, EP_, 1>(tmA, tmB, p, num_tiles, stream);              \
+  // Epilogue-heavy launches (RoPE, GELU, fp32 residual with a short K loop) get 16 epilogue warps (4 per scheduler)
+  // so that TMEM-load / global-load latencies overlap; mainloop-bound launches keep 8 warps and a deeper smem ring.
+  static int ew_override = -1;
+  if (ew_override < 0) {
+    const char* e = getenv("STA_GEMM_EPI_WARPS");
+    ew_override = e ? atoi(e) : 0;
   }
+  int ew = (g.epi == EPI_ROPE || g.epi == EPI_GELU || (g.epi == EPI_F32 && p.K <= 1536)) ? 16 : 8;
+  if (ew_override == 8 || ew_override == 16) ew = ew_override;
+  if (g.epi == EPI_HEAD || g.epi == EPI_PIXSHUF || g.amode == A_CONV3 || bn != 256) ew = 8;
 
+#define STA_GEMM_CASE2(BN_, AM_, EP_, EW_)                                                  \
+  if (bn == BN_ && g.amode == AM_ && g.epi == EP_ && ew == EW_) {                           \
+    if (cg == 2) return launch_inst<BN_, AM_, EP_, 2, EW_>(tmA, tmB, p, num_tiles, stream); \
+    return launch_inst<BN_, AM_, EP_, 1, EW_>(tmA, tmB, p, num_tiles, stream);              \
+  }
+#define STA_GEMM_CASE(BN_, AM_, EP_) STA_GEMM_CASE2(BN_, AM_, EP_, 8)
+
+  STA_GEMM_CASE2(256, A_LINEAR, EPI_GELU, 16)
+  STA_GEMM_CASE2(256, A_LINEAR, EPI_F32, 16)
+  STA_GEMM_CASE2(256, A_LINEAR, EPI_ROPE, 16)
+  STA_GEMM_CASE2(256, A_LINEAR, EPI_BF16, 16)
   STA_GEMM_CASE(256, A_LINEAR, EPI_BF16)
   STA_GEMM_CASE(256, A_LINEAR, EPI_GELU)
   STA_GEMM_CASE(256, A_LINEAR, EPI_F32)
@@ -103,6 +123,7 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
   STA_GEMM_CASE(128, A_CONV3, EPI_BF16)
   STA_GEMM_CASE(128, A_CONV3, EPI_HEAD)
 #undef STA_GEMM_CASE
+#undef STA_GEMM_CASE2
   set_last_error("launch_gemm: unsupported (BN, amode, epilogue) combination");
   return 2;
 }

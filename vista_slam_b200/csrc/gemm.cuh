@@ -2,8 +2,8 @@
 //
 //   D[M,N] = A[M,K] * W[N,K]^T  (bf16 operands, fp32 accumulation in TMEM)
 //
-// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected
-// thread issues tcgen05.mma), warp 2 = TMEM allocator, warps 4..11 = epilogue
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread issues tcgen05.mma),
+// warp 2 = TMEM allocator, warps 4.. = 8 or 16 epilogue warps
 // (TMEM -> registers -> fused epilogue -> global).  The accumulator is double
 // buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // mainloop of tile i+1.  Operand tiles are 128B-swizzled K-major [rows][64]
@@ -47,6 +47,7 @@ struct GemmParams {
   const int* pos;         // [M][2] (y, x)
   int rope_cols;
   int rope_max_pos;
+  int rope_smem_rows;  // > 0: table rows for positions [-1, rope_smem_rows - 2] are staged in shared memory
   // EPI_PIXSHUF
   int ps_k, ps_cout, ps_h, ps_w;
   // EPI_HEAD
@@ -54,32 +55,40 @@ struct GemmParams {
   const float* head_b;  // [4]
   float* pts3d;         // [pixels][3]
   float* conf;          // [pixels]
+  long long* dbg;       // optional clock64 trace (env STA_GEMM_TRACE), else null
 };
 
 // CG = 1: one CTA per 128 x BN tile (tcgen05 cta_group::1).
 // CG = 2: a CTA pair (cluster of 2 on one TPC) per 256 x BN tile (cta_group::2): each CTA stages its own
 //         128 rows of A and BN/2 rows of B, so per-SM shared-memory traffic per MMA is halved for B.
-template <int BN, int CG>
+template <int BN, int CG, int EW>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = (BN / CG) * BK * 2;
   static constexpr uint32_t BAR_BYTES = 256;
-  static constexpr uint32_t EPI_SMEM_BYTES = 128 * 4 * sizeof(float);  // EPI_HEAD partial sums
-  static constexpr uint32_t STG_BYTES = 8 * 32 * 36 * sizeof(float);   // 8 epilogue warps x [32][36] fp32 staging
+  static constexpr int EPI_WARPS = EW;  // 8 (mainloop-bound launches) or 16 (epilogue-heavy: 4 warps per scheduler)
+  static constexpr int PARTS = EW / 4;  // column parts of a tile, one per epilogue warp of a lane quarter
+  static constexpr uint32_t EPI_SMEM_BYTES = 3 * 128 * 4 * sizeof(float);  // EPI_HEAD partial sums of parts 1..
+  static constexpr uint32_t STG_BYTES = EPI_WARPS * 32 * 36 * sizeof(float);  // per-warp [32][36] fp32 staging
+  static constexpr int ROPE_SMEM_ROWS = 64;                            // positions -1 .. 62
+  static constexpr uint32_t ROPE_SMEM_BYTES = ROPE_SMEM_ROWS * 32 * sizeof(float);
   static constexpr uint32_t MAX_SMEM = 227 * 1024;
-  static constexpr int STAGES_FIT = (MAX_SMEM - BAR_BYTES - EPI_SMEM_BYTES - STG_BYTES) / (A_BYTES + B_BYTES);
-  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;  // 3 / 5 (CG=1), 5 / 7 (CG=2)
-  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + EPI_SMEM_BYTES + STG_BYTES;
-  static constexpr int THREADS = 384;
-  static constexpr int EPI_THREADS = 256;
+  static constexpr int STAGES_FIT =
+      (MAX_SMEM - BAR_BYTES - EPI_SMEM_BYTES - STG_BYTES - ROPE_SMEM_BYTES) / (A_BYTES + B_BYTES);
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;  // 3 / 4 (CG=1), 4 / 6 (CG=2)
+  static constexpr uint32_t SMEM_BYTES =
+      STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + EPI_SMEM_BYTES + STG_BYTES + ROPE_SMEM_BYTES;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr int EPI_THREADS = 32 * EPI_WARPS;
   static_assert(STAGES <= 8, "barrier area holds at most 8 stages");
 };
 
 // ---------------------------------------------------------------------------
-// Epilogue for one 128 x BN accumulator tile; executed by the 8 epilogue warps.
-// warp (quarter, half): TMEM lanes [32*quarter, +32), columns [half*BN/2, +BN/2).
+// Epilogue for one 128 x BN accumulator tile; executed by the 16 epilogue warps (4 per scheduler, so that the
+// global-load / TMEM-load latencies of one warp are covered by the others).
+// warp (quarter, part): TMEM lanes [32*quarter, +32), columns [part*BN/4, +BN/4).
 //
 // tcgen05.ld (32x32b) hands every thread one accumulator ROW (32 consecutive columns).  Storing
 // that way would make each warp store touch 32 different cache lines, so every 32x32 fp32 chunk
@@ -123,23 +132,29 @@ __device__ __forceinline__ void add_bf16x4(float4& v, uint2 q) {
   v.x += bf16_lo(q.x); v.y += bf16_hi(q.x); v.z += bf16_lo(q.y); v.w += bf16_hi(q.y);
 }
 
-template <int BN, int AMODE, int EPI>
+template <int BN, int AMODE, int EPI, int EW>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int m_tile, int n_tile,
-                                              int quarter, int half, float* epi_smem, float* stg) {
-  constexpr int CH = BN / 2;
+                                              int quarter, int part, float* epi_smem, float* stg,
+                                              const float* rope_s, uint64_t* tfull_bar, uint32_t tfull_phase) {
+  // Everything that does not depend on the accumulator (row bookkeeping, positions, residual prefetch) is done
+  // BEFORE waiting for the tile's MMAs, so its global-memory latency hides behind the mainloop.
+  constexpr int PARTS = EW / 4;
+  constexpr int CH = BN / PARTS;  // columns per epilogue warp
   const int lane = threadIdx.x & 31;
-  const int colbase = n_tile * BN + half * CH;
+  const int colbase = n_tile * BN + part * CH;
 
   if constexpr (EPI == EPI_HEAD) {
     // head.2 epilogue: ReLU -> head.4 (1x1, 128 -> 4) -> postprocess (dpt_block.py:319-323,
-    // postprocess.py:10-62).  Row mapping: each thread owns 64 of the 128 channels of one pixel; the two
-    // column halves are combined through shared memory.  Nothing but 16 bytes per pixel is written.
+    // postprocess.py:10-62).  Row mapping: each thread owns 32 of the 128 channels of one pixel; the four
+    // column parts are combined through shared memory.  Nothing but 16 bytes per pixel is written.
     static_assert(BN == 128, "EPI_HEAD expects the 128-channel head");
+    mbar_wait(tfull_bar, tfull_phase);
+    tc_fence_after();
     const int r_local = quarter * 32 + lane;
     long long orow;
     bool valid;
     tile_row<AMODE>(p, m_tile, r_local, orow, valid);
-    float part[4] = {0.f, 0.f, 0.f, 0.f};
+    float psum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int c = 0; c < CH; c += 32) {
       const int col = colbase + c;
@@ -151,20 +166,26 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
       for (int i = 0; i < 32; ++i) {
         float v = fmaxf(__uint_as_float(acc[i]) + __ldg(p.bias + col + i), 0.0f);
         float4 w4 = __ldg(wp + i);
-        part[0] = fmaf(v, w4.x, part[0]);
-        part[1] = fmaf(v, w4.y, part[1]);
-        part[2] = fmaf(v, w4.z, part[2]);
-        part[3] = fmaf(v, w4.w, part[3]);
+        psum[0] = fmaf(v, w4.x, psum[0]);
+        psum[1] = fmaf(v, w4.y, psum[1]);
+        psum[2] = fmaf(v, w4.z, psum[2]);
+        psum[3] = fmaf(v, w4.w, psum[3]);
       }
     }
-    if (half == 1) reinterpret_cast<float4*>(epi_smem)[r_local] = make_float4(part[0], part[1], part[2], part[3]);
-    named_bar_sync(1, 256);
-    if (half == 0) {
+    if (part != 0)
+      reinterpret_cast<float4*>(epi_smem)[(part - 1) * 128 + r_local] = make_float4(psum[0], psum[1], psum[2], psum[3]);
+    named_bar_sync(1, 32 * EW);
+    if (part == 0) {
       float4 o = reinterpret_cast<float4*>(epi_smem)[r_local];
-      const float x = part[0] + o.x + __ldg(p.head_b + 0);
-      const float y = part[1] + o.y + __ldg(p.head_b + 1);
-      const float z = part[2] + o.z + __ldg(p.head_b + 2);
-      const float cf = part[3] + o.w + __ldg(p.head_b + 3);
+#pragma unroll
+      for (int q = 1; q < PARTS - 1; ++q) {
+        const float4 t = reinterpret_cast<float4*>(epi_smem)[q * 128 + r_local];
+        o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+      }
+      const float x = psum[0] + o.x + __ldg(p.head_b + 0);
+      const float y = psum[1] + o.y + __ldg(p.head_b + 1);
+      const float z = psum[2] + o.z + __ldg(p.head_b + 2);
+      const float cf = psum[3] + o.w + __ldg(p.head_b + 3);
       if (valid) {
         const float d = sqrtf(x * x + y * y + z * z);
         const float dc = fmaxf(d, 1e-8f);
@@ -175,7 +196,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
         p.conf[orow] = 1.0f + expf(cf);
       }
     }
-    named_bar_sync(1, 256);
+    named_bar_sync(1, 32 * EW);
     return;
   } else {
     // ---- coalesced mapping bookkeeping: this lane touches rows 4*it + (lane>>3), it = 0..7 ----
@@ -205,6 +226,24 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
       }
     }
 
+    // EPI_ROPE: (y, x) token positions of this lane's 8 rows
+    [[maybe_unused]] int pos_y[8], pos_x[8];
+    if constexpr (EPI == EPI_ROPE) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        int py = 0, px = 0;
+        if ((vmask >> it) & 1u) {
+          const int2 pp = *reinterpret_cast<const int2*>(p.pos + 2 * orow_c[it]);
+          py = pp.x;
+          px = pp.y;
+          if (py < -1 || py > p.rope_max_pos || px < -1 || px > p.rope_max_pos)
+            device_fatal("token position outside the RoPE table");
+        }
+        pos_y[it] = py;
+        pos_x[it] = px;
+      }
+    }
+
     // flush one staged 32-column chunk (global columns [col, col+32)) in the coalesced mapping
     auto flush = [&](int col) {
       if (col >= p.N) return;
@@ -218,161 +257,153 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
         const int kw = kk - kh * p.ps_k;
         pix_off = static_cast<long long>(kh) * (p.ps_w * p.ps_k) + kw;
         b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co + cc));
-      } else if constexpr (EPI != EPI_ROPE) {  // RoPE adds its bias before rotating (row mapping)
+      } else {
         if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + cc));
       }
-      // Residual loads are issued up front: the in-place residual stream (resid == out) would otherwise force
-      // load -> store -> load ordering (possible aliasing) and serialise ~800-cycle DRAM round trips.
-      [[maybe_unused]] float4 rf[8];
-      [[maybe_unused]] uint2 ra[8], rb[8];
-      if constexpr (EPI == EPI_F32) {
-        if (p.resid) {
+      // Residual loads are issued ahead of the stores, four rows at a time: the in-place residual stream
+      // (resid == out) would otherwise force load -> store -> load ordering (possible aliasing) and serialise
+      // ~1 us DRAM round trips.
 #pragma unroll
-          for (int it = 0; it < 8; ++it)
-            rf[it] = ((vmask >> it) & 1u)
-                         ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.resid) +
-                                                            orow_c[it] * p.ldo + col + cc)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      if constexpr (EPI == EPI_BF16) {
-        if (p.resid) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it)
-            ra[it] = ((vmask >> it) & 1u)
-                         ? *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) +
-                                                           orow_c[it] * p.ldo + col + cc)
-                         : make_uint2(0u, 0u);
-        }
-        if (p.resid2) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it)
-            rb[it] = ((vmask >> it) & 1u)
-                         ? *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.resid2) +
-                                                           orow_c[it] * p.ldo + col + cc)
-                         : make_uint2(0u, 0u);
-        }
-      }
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        float4 v = *reinterpret_cast<const float4*>(stg + (it * 4 + crow) * kStageLd + cc);
-        if (!((vmask >> it) & 1u)) continue;
-        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+      for (int hb = 0; hb < 2; ++hb) {
+        [[maybe_unused]] float4 rf[4];
+        [[maybe_unused]] uint2 ra[4], rb[4];
         if constexpr (EPI == EPI_F32) {
-          float* op = reinterpret_cast<float*>(p.out) + orow_c[it] * p.ldo + col + cc;
-          if (p.resid) { v.x += rf[it].x; v.y += rf[it].y; v.z += rf[it].z; v.w += rf[it].w; }
-          *reinterpret_cast<float4*>(op) = v;
-        } else if constexpr (EPI == EPI_PIXSHUF) {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (orow_c[it] + pix_off) * p.ps_cout + co + cc;
-          *reinterpret_cast<uint2*>(op) = pack4_bf16(v);
-        } else {
-          const long long off = orow_c[it] * p.ldo + col + cc;
-          if constexpr (EPI == EPI_BF16) {
-            if (p.resid) add_bf16x4(v, ra[it]);
-            if (p.resid2) add_bf16x4(v, rb[it]);
-            if (p.relu_main) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if (p.resid) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int it = hb * 4 + k;
+              rf[k] = ((vmask >> it) & 1u)
+                          ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.resid) +
+                                                             orow_c[it] * p.ldo + col + cc)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
-          if constexpr (EPI == EPI_GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-          if (p.out) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = pack4_bf16(v);
-          if constexpr (EPI == EPI_BF16) {
-            if (p.out2) {
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + off) = pack4_bf16(v);
+        }
+        if constexpr (EPI == EPI_BF16) {
+          if (p.resid) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int it = hb * 4 + k;
+              ra[k] = ((vmask >> it) & 1u)
+                          ? *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) +
+                                                            orow_c[it] * p.ldo + col + cc)
+                          : make_uint2(0u, 0u);
+            }
+          }
+          if (p.resid2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int it = hb * 4 + k;
+              rb[k] = ((vmask >> it) & 1u)
+                          ? *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.resid2) +
+                                                            orow_c[it] * p.ldo + col + cc)
+                          : make_uint2(0u, 0u);
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // straight-line body: only the global loads / stores are predicated on row validity, so the
+          // compiler can interleave the four rows of a batch
+          const int it = hb * 4 + k;
+          const bool ok = (vmask >> it) & 1u;
+          float4 v = *reinterpret_cast<const float4*>(stg + (it * 4 + crow) * kStageLd + cc);
+          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          if constexpr (EPI == EPI_ROPE) {
+            // 2-D RoPE (pos_embed/pos_embed.py:149-185, curope/kernels.cu:17-82).  A 32-column chunk is exactly
+            // one half of a 64-wide head: the y-half (rotated by pos_y) or the x-half (pos_x).  Inside a half the
+            // pairs are (i, i+16): the partner columns live in lane ^ 4 of the same row group.
+            if (col < p.rope_cols) {  // uniform per chunk: the V columns are not rotated
+              const float4 w = make_float4(__shfl_xor_sync(0xffffffffu, v.x, 4), __shfl_xor_sync(0xffffffffu, v.y, 4),
+                                           __shfl_xor_sync(0xffffffffu, v.z, 4), __shfl_xor_sync(0xffffffffu, v.w, 4));
+              const int pz = ((col >> 5) & 1) ? pos_x[it] : pos_y[it];
+              const int ps = min(pz + 1, p.rope_smem_rows - 1);  // clamped shared-memory row (always safe to read)
+              const float4* tb = reinterpret_cast<const float4*>(rope_s + ps * 32) + ((cc & 15) >> 1);
+              float4 t0 = tb[0];  // (cos f, sin f, cos f+1, sin f+1)
+              float4 t1 = tb[1];  // (cos f+2, sin f+2, cos f+3, sin f+3)
+              if (pz + 1 >= p.rope_smem_rows) {  // beyond the staged rows (very large images): global table
+                const float4* tg =
+                    reinterpret_cast<const float4*>(p.rope_tab + static_cast<long long>(pz + 1) * 32) + ((cc & 15) >> 1);
+                t0 = __ldg(tg);
+                t1 = __ldg(tg + 1);
+              }
+              const float sg = (cc & 16) ? 1.0f : -1.0f;  // lower 16: u*cos - w*sin ; upper 16: u*cos + w*sin
+              v.x = fmaf(sg * w.x, t0.y, v.x * t0.x);
+              v.y = fmaf(sg * w.y, t0.w, v.y * t0.z);
+              v.z = fmaf(sg * w.z, t1.y, v.z * t1.x);
+              v.w = fmaf(sg * w.w, t1.w, v.w * t1.z);
+            }
+          }
+          if constexpr (EPI == EPI_F32) {
+            float* op = reinterpret_cast<float*>(p.out) + orow_c[it] * p.ldo + col + cc;
+            if (p.resid) { v.x += rf[k].x; v.y += rf[k].y; v.z += rf[k].z; v.w += rf[k].w; }
+            if (ok) *reinterpret_cast<float4*>(op) = v;
+          } else if constexpr (EPI == EPI_PIXSHUF) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (orow_c[it] + pix_off) * p.ps_cout + co + cc;
+            if (ok) *reinterpret_cast<uint2*>(op) = pack4_bf16(v);
+          } else {
+            const long long off = orow_c[it] * p.ldo + col + cc;
+            if constexpr (EPI == EPI_BF16) {
+              if (p.resid) add_bf16x4(v, ra[k]);
+              if (p.resid2) add_bf16x4(v, rb[k]);
+              if (p.relu_main) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            }
+            if constexpr (EPI == EPI_GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+            if (p.out && ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = pack4_bf16(v);
+            if constexpr (EPI == EPI_BF16) {
+              if (p.out2 && ok) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + off) = pack4_bf16(v);
+              }
             }
           }
         }
       }
     };
 
-    if constexpr (EPI == EPI_ROPE) {
-      static_assert(CH % 64 == 0, "RoPE epilogue works on whole 64-wide heads");
-      // row mapping: bias + 2-D RoPE (rotate-half inside each 32-wide half of the head; reference:
-      // pos_embed/pos_embed.py:149-185, curope/kernels.cu:17-82), then staged out like everything else
-      long long orow_r;
-      bool valid_r;
-      tile_row<AMODE>(p, m_tile, quarter * 32 + lane, orow_r, valid_r);
-      int py = 0, px = 0;
-      if (valid_r) {
-        py = p.pos[2 * orow_r + 0];
-        px = p.pos[2 * orow_r + 1];
-        if (py < -1 || py > p.rope_max_pos || px < -1 || px > p.rope_max_pos)
-          device_fatal("token position outside the RoPE table");
-      }
-      const float4* ty = reinterpret_cast<const float4*>(p.rope_tab + static_cast<long long>(py + 1) * 32);
-      const float4* tx = reinterpret_cast<const float4*>(p.rope_tab + static_cast<long long>(px + 1) * 32);
-#pragma unroll 1
-      for (int c = 0; c < CH; c += 64) {
-        const int col = colbase + c;
-        uint32_t a0[32], a1[32];
-        tmem_ld32(taddr + c, a0);
-        tmem_ld32(taddr + c + 32, a1);
-        tmem_ld_wait();
-        float v[64];
+    // L2 prefetch of the residual rows this lane will add (fp32 residual stream / bf16 skip tensors)
+    if constexpr (EPI == EPI_F32 || EPI == EPI_BF16) {
+      if (p.resid) {
+        constexpr int esz = (EPI == EPI_F32) ? 4 : 2;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] = __uint_as_float(a0[i]);
-          v[32 + i] = __uint_as_float(a1[i]);
-        }
-        if (col < p.N) {
-          if (p.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+        for (int it = 0; it < 8; ++it) {
+          if ((vmask >> it) & 1u) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float4 b = __ldg(bp + j);
-              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            }
-          }
-          if (col < p.rope_cols) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 t = __ldg(ty + j);  // (cos_{2j}, sin_{2j}, cos_{2j+1}, sin_{2j+1})
-              float u0 = v[2 * j], w0 = v[2 * j + 16];
-              v[2 * j] = u0 * t.x - w0 * t.y;
-              v[2 * j + 16] = w0 * t.x + u0 * t.y;
-              float u1 = v[2 * j + 1], w1 = v[2 * j + 17];
-              v[2 * j + 1] = u1 * t.z - w1 * t.w;
-              v[2 * j + 17] = w1 * t.z + u1 * t.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 t = __ldg(tx + j);
-              float u0 = v[32 + 2 * j], w0 = v[32 + 2 * j + 16];
-              v[32 + 2 * j] = u0 * t.x - w0 * t.y;
-              v[32 + 2 * j + 16] = w0 * t.x + u0 * t.y;
-              float u1 = v[32 + 2 * j + 1], w1 = v[32 + 2 * j + 17];
-              v[32 + 2 * j + 1] = u1 * t.z - w1 * t.w;
-              v[32 + 2 * j + 17] = w1 * t.z + u1 * t.w;
+            for (int c = 0; c < CH; c += 32) {
+              if (colbase + c < p.N) {
+                const char* a = reinterpret_cast<const char*>(p.resid) + (orow_c[it] * p.ldo + colbase + c + cc) * esz;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                if constexpr (EPI == EPI_BF16) {
+                  if (p.resid2) {
+                    const char* a2 = reinterpret_cast<const char*>(p.resid2) + (orow_c[it] * p.ldo + colbase + c + cc) * esz;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a2));
+                  }
+                }
+              }
             }
           }
         }
-        stage_store32(stg, lane, v);
-        __syncwarp();
-        flush(col);
-        __syncwarp();
-        stage_store32(stg, lane, v + 32);
-        __syncwarp();
-        flush(col + 32);
-        __syncwarp();
       }
-    } else {
+    }
+    mbar_wait(tfull_bar, tfull_phase);
+    tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < CH; c += 32) {
-        uint32_t acc[32];
-        tmem_ld32(taddr + c, acc);
-        tmem_ld_wait();
-        stage_store32(stg, lane, reinterpret_cast<const float*>(acc));
-        __syncwarp();
-        flush(colbase + c);
-        __syncwarp();
-      }
+    for (int c = 0; c < CH; c += 32) {
+      uint32_t acc[32];
+      tmem_ld32(taddr + c, acc);
+      tmem_ld_wait();
+      stage_store32(stg, lane, reinterpret_cast<const float*>(acc));
+      __syncwarp();
+      flush(colbase + c);
+      __syncwarp();
     }
   }
 }
 
-template <int BN, int AMODE, int EPI, int CG>
-__global__ void __launch_bounds__(384, 1)
+template <int BN, int AMODE, int EPI, int CG, int EW>
+__global__ void __launch_bounds__(GemmCfg<BN, CG, EW>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, EW>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr uint32_t A_BYTES = Cfg::A_BYTES;
   constexpr uint32_t B_BYTES = Cfg::B_BYTES;
@@ -388,6 +419,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* epi_smem = reinterpret_cast<float*>(smem + STAGES * (A_BYTES + B_BYTES) + Cfg::BAR_BYTES);
   float* stg_all = reinterpret_cast<float*>(smem + STAGES * (A_BYTES + B_BYTES) + Cfg::BAR_BYTES + Cfg::EPI_SMEM_BYTES);
+  float* rope_s = stg_all + Cfg::EPI_WARPS * kStageFloatsPerWarp;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -412,13 +444,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 8 * CG);  // 8 epilogue warps per CTA, all arriving on the leader's barrier
-    mbar_init(&tempty[1], 8 * CG);
+    mbar_init(&tempty[0], Cfg::EPI_WARPS * CG);  // every epilogue warp of the pair arrives on the leader's barrier
+    mbar_init(&tempty[1], Cfg::EPI_WARPS * CG);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+  }
+  if constexpr (EPI == EPI_ROPE) {
+    // the sin/cos table is a constant of the library (not produced by the previous kernel): stage the rows for
+    // small positions in shared memory before the PDL wait
+    if (warp >= 4) {
+      const int nfl = p.rope_smem_rows * 32;
+      for (int i = (threadIdx.x - 128) * 4; i < nfl; i += Cfg::EPI_THREADS * 4)
+        *reinterpret_cast<float4*>(rope_s + i) = __ldg(reinterpret_cast<const float4*>(p.rope_tab + i));
+    }
   }
   if (warp == 2) {
     if constexpr (CG == 2) {
@@ -489,7 +530,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int tcount = (tile - first_tile) / tile_step;
+        const bool trc = p.dbg && blockIdx.x == 0 && tcount < 40;
+        if (trc) p.dbg[256 + 4 * tcount + 0] = clock64();
         mbar_wait(&tempty[acc], acc_phase ^ 1);
+        if (trc) p.dbg[256 + 4 * tcount + 1] = clock64();
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < nkb; ++kb) {
@@ -509,6 +554,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if constexpr (CG == 2) umma_commit_cg2(&tfull[acc]); else umma_commit(&tfull[acc]);
+        if (trc) p.dbg[256 + 4 * tcount + 2] = clock64();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -516,17 +562,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     // ============ epilogue warps (every CTA drains its own 128 accumulator rows) ============
     const int quarter = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int part = (warp - 4) >> 2;  // which quarter of the tile's columns
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       const int m_tile = (tile / n_tiles) * CG + static_cast<int>(cta_rank);
       const int n_tile = tile % n_tiles;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2);
-      epilogue_tile<BN, AMODE, EPI>(p, taddr, m_tile, n_tile, quarter, half, epi_smem,
-                                    stg_all + (warp - 4) * kStageFloatsPerWarp);
+      const int tcount = (tile - first_tile) / tile_step;
+      const bool trc = p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && tcount < 40;
+      if (trc) p.dbg[4 * tcount + 0] = clock64();
+      if (trc) p.dbg[4 * tcount + 1] = clock64();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + part * (BN / Cfg::PARTS);
+      epilogue_tile<BN, AMODE, EPI, EW>(p, taddr, m_tile, n_tile, quarter, part, epi_smem,
+                                    stg_all + (warp - 4) * kStageFloatsPerWarp, rope_s, &tfull[acc], acc_phase);
+      if (trc) p.dbg[4 * tcount + 2] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

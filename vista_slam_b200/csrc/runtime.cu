@@ -446,6 +446,7 @@ int linear(const Ctx& c, int epi, const bf16* A, int M, const Lin& L, void* out,
       set_last_error("failed to build the RoPE table");
       return 1;
     }
+    p.rope_smem_rows = 64;  // positions -1..62 from shared memory, larger ones from the global table
   }
   return gemm(c, A_LINEAR, epi, A, L.K, L, p);
 }
@@ -1239,6 +1240,7 @@ int sta_op_gemm(const StaGemmDesc* d, void* stream) {
       set_last_error("failed to build the RoPE table");
       return 1;
     }
+    p.rope_smem_rows = 64;
   }
   p.ps_k = d->ps_k; p.ps_cout = d->ps_cout; p.ps_h = d->ps_h; p.ps_w = d->ps_w;
   p.head_w = d->head_w; p.head_b = d->head_b; p.pts3d = d->pts3d; p.conf = d->conf;
