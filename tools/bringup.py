@@ -116,6 +116,13 @@ def group_gemm_epi():
     x0 = x.clone()
     run_gemm(gemm_desc(epi=EPI_F32, A=A, lda=K, W=W, ldw=K, M=M, N=N, K=K, bias=bias, out=x, ldo=N, resid=x))
     report("epi f32 resid in place", x, x0 + base, 2e-3)
+    # F32 without residual (plain fp32 store) and with a separate residual tensor
+    y = torch.zeros(M, N, device=dev)
+    run_gemm(gemm_desc(epi=EPI_F32, A=A, lda=K, W=W, ldw=K, M=M, N=N, K=K, bias=bias, out=y, ldo=N))
+    report("epi f32 no resid", y, base, 2e-3)
+    y = torch.zeros(M, N, device=dev)
+    run_gemm(gemm_desc(epi=EPI_F32, A=A, lda=K, W=W, ldw=K, M=M, N=N, K=K, bias=bias, out=y, ldo=N, resid=x0))
+    report("epi f32 resid separate", y, x0 + base, 2e-3)
     # F32 with rowmap (decoder_embed): 7 samples x 111 tokens
     nt = 111
     xd = torch.zeros(7 * (nt + 1), N, device=dev)
@@ -347,7 +354,8 @@ def main():
         import torch
         torch.backends.cuda.matmul.allow_tf32 = False
         torch.backends.cudnn.allow_tf32 = False
-        globals()["group_" + sys.argv[1]]()
+        for g in sys.argv[1:]:
+            globals()["group_" + g]()
         return
     for g in GROUPS:
         print("=== group %s ===" % g, flush=True)

@@ -30,3 +30,9 @@ for t in range(16):
     e = [x - t0 for x in b[4 * t:4 * t + 3]]
     m = [x - t0 for x in b[256 + 4 * t:256 + 4 * t + 3]]
     print(t, e, " | ", m)
+print("TMA epilogue fine trace (warp 4): per tile: t(tfull) then per chunk [tmem+bias ready, math done, store issued] relative to tfull")
+for t in range(2, 8):
+    r = b[512 + 16 * t: 512 + 16 * t + 13]
+    if r[0] <= 0:
+        continue
+    print(t, r[0] - t0, [x - r[0] for x in r[1:] if x > 0])

@@ -128,9 +128,23 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// global[box] += smem[box] (element type of the tensor map), performed by the L2 reduction units
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the bulk stores of this thread have finished READING shared memory (buffer reusable)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------
@@ -324,20 +338,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// Exact (erf) GELU, nn.GELU() default (sta_blocks.py:60,68), branch-free:
-// erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z), z >= 0  (Abramowitz & Stegun 7.1.26,
-// |error| <= 1.5e-7, i.e. below fp32 rounding of the GEMM accumulator and far below the bf16 output step).
+// Exact (erf) GELU, nn.GELU() default (sta_blocks.py:60,68), branch-free and to fp32 rounding level
+// (tools/fit_gelu.py reproduces the coefficients and the error bound).
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  poly *= t;
-  const float e = ex2_approx(x * x * -0.72134752044448170f);  // exp(-x^2 / 2)
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  // gelu(x) = x * Phi(x) = max(x, 0) - |x| * Phi(-|x|),  Phi(-a) = 0.5 * erfc(a / sqrt(2)) = 2^q(a).
+  // q is a degree-6 fit of log2(Phi(-a)) on [0, 6] (Phi(-6) = 1e-9; larger |x| are clamped): one MUFU.EX2 and
+  // ten FP32 ops per element, max |error| 5e-7 against the erf form over [-9, 9] (fp32 rounding level).
+  const float a = fminf(fabsf(x), 6.0f);
+  float q = fmaf(a, 3.4195283660665154e-05f, -0.0007779477164149284f);
+  q = fmaf(a, q, 0.008105806075036526f);
+  q = fmaf(a, q, -0.053442906588315964f);
+  q = fmaf(a, q, -0.4587582051753998f);
+  q = fmaf(a, q, -1.1511993408203125f);
+  q = fmaf(a, q, -0.9999947547912598f);
+  return fmaf(-fabsf(x), ex2_approx(q), fmaxf(x, 0.0f));
 }
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {

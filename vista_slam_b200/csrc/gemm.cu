@@ -7,11 +7,11 @@
 
 namespace sta {
 
-template <int BN, int AMODE, int EPI, int CG, int EW>
-static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_tiles,
-                       cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG, EW>;
-  auto kern = gemm_tc_kernel<BN, AMODE, EPI, CG, EW>;
+template <int BN, int AMODE, int EPI, int CG, int EW, bool TMA>
+static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                       int num_tiles, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CG, EW, EPI, TMA>;
+  auto kern = gemm_tc_kernel<BN, AMODE, EPI, CG, EW, TMA>;
   static bool attr_set = false;
   if (!attr_set) {
     STA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
@@ -21,7 +21,7 @@ static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   const int max_items = num_sms() / CG;
   const int items = num_tiles < max_items ? num_tiles : max_items;
   if (items < 1) return 0;
-  STA_CHECK_CUDA(launch_pdl(kern, dim3(items * CG), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, CG, tmA, tmB, p));
+  STA_CHECK_CUDA(launch_pdl(kern, dim3(items * CG), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, CG, tmA, tmB, tmC, p));
   return 0;
 }
 
@@ -90,28 +90,48 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
   const int n_tiles = (p.N + bn - 1) / bn;
   const int num_tiles = ((m_tiles + cg - 1) / cg) * n_tiles;
 
-  // Epilogue-heavy launches (RoPE, GELU, fp32 residual with a short K loop) get 16 epilogue warps (4 per scheduler)
-  // so that TMEM-load / global-load latencies overlap; mainloop-bound launches keep 8 warps and a deeper smem ring.
-  static int ew_override = -1;
-  if (ew_override < 0) {
-    const char* e = getenv("STA_GEMM_EPI_WARPS");
-    ew_override = e ? atoi(e) : 0;
+  // TMA-store epilogue (epilogue_tile_tma) for the wide linear layers: bf16 / GELU / RoPE outputs without skip
+  // tensors, fp32 outputs that either have no residual or accumulate in place (out += ..., bulk reduce-add).
+  static int tma_mode = -1;
+  if (tma_mode < 0) {
+    const char* e = getenv("STA_GEMM_TMA_EPI");  // 0 disables (A/B timing and debugging)
+    tma_mode = (e && e[0] == '0') ? 0 : 1;
   }
-  int ew = (g.epi == EPI_ROPE || g.epi == EPI_GELU || (g.epi == EPI_F32 && p.K <= 1536)) ? 16 : 8;
-  if (ew_override == 8 || ew_override == 16) ew = ew_override;
-  if (g.epi == EPI_HEAD || g.epi == EPI_PIXSHUF || g.amode == A_CONV3 || bn != 256) ew = 8;
-
-#define STA_GEMM_CASE2(BN_, AM_, EP_, EW_)                                                  \
-  if (bn == BN_ && g.amode == AM_ && g.epi == EP_ && ew == EW_) {                           \
-    if (cg == 2) return launch_inst<BN_, AM_, EP_, 2, EW_>(tmA, tmB, p, num_tiles, stream); \
-    return launch_inst<BN_, AM_, EP_, 1, EW_>(tmA, tmB, p, num_tiles, stream);              \
+  bool tma = tma_mode == 1 && bn == 256 && g.amode == A_LINEAR && p.out != nullptr && p.out2 == nullptr;
+  const int esz = (g.epi == EPI_F32) ? 4 : 2;
+  tma = tma && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * esz) % 16 == 0;
+  p.c_reduce = 0;
+  if (g.epi == EPI_BF16) {
+    tma = tma && p.resid == nullptr && p.resid2 == nullptr;
+  } else if (g.epi == EPI_F32) {
+    tma = tma && p.rowmap_n == 0 && (p.resid == nullptr || p.resid == p.out);
+    p.c_reduce = (p.resid != nullptr) ? 1 : 0;
+  } else if (g.epi != EPI_GELU && g.epi != EPI_ROPE) {
+    tma = false;
   }
-#define STA_GEMM_CASE(BN_, AM_, EP_) STA_GEMM_CASE2(BN_, AM_, EP_, 8)
+  CUtensorMap tmC = tmA;
+  if (tma) {
+    uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M};
+    uint64_t strides[1] = {(uint64_t)p.ldo * esz};
+    uint32_t box[2] = {(uint32_t)(128 / esz), 32};
+    if (make_tmap(&tmC, p.out, esz == 4, 2, dims, strides, box)) return 1;
+  }
 
-  STA_GEMM_CASE2(256, A_LINEAR, EPI_GELU, 16)
-  STA_GEMM_CASE2(256, A_LINEAR, EPI_F32, 16)
-  STA_GEMM_CASE2(256, A_LINEAR, EPI_ROPE, 16)
-  STA_GEMM_CASE2(256, A_LINEAR, EPI_BF16, 16)
+  // 8 epilogue warps everywhere: with the TMA-store epilogue every fused epilogue of the trunk fits under the
+  // K >= 768 mainloop, and the smaller CTA keeps a 5-deep operand ring (16 warps were measured slower end to end).
+  const int ew = 8;
+
+#define STA_GEMM_CASE3(BN_, AM_, EP_, EW_, TMA_)                                                       \
+  if (bn == BN_ && g.amode == AM_ && g.epi == EP_ && ew == EW_ && tma == TMA_) {                       \
+    if (cg == 2) return launch_inst<BN_, AM_, EP_, 2, EW_, TMA_>(tmA, tmB, tmC, p, num_tiles, stream); \
+    return launch_inst<BN_, AM_, EP_, 1, EW_, TMA_>(tmA, tmB, tmC, p, num_tiles, stream);              \
+  }
+#define STA_GEMM_CASE(BN_, AM_, EP_) STA_GEMM_CASE3(BN_, AM_, EP_, 8, false)
+
+  STA_GEMM_CASE3(256, A_LINEAR, EPI_GELU, 8, true)
+  STA_GEMM_CASE3(256, A_LINEAR, EPI_F32, 8, true)
+  STA_GEMM_CASE3(256, A_LINEAR, EPI_ROPE, 8, true)
+  STA_GEMM_CASE3(256, A_LINEAR, EPI_BF16, 8, true)
   STA_GEMM_CASE(256, A_LINEAR, EPI_BF16)
   STA_GEMM_CASE(256, A_LINEAR, EPI_GELU)
   STA_GEMM_CASE(256, A_LINEAR, EPI_F32)
@@ -123,7 +143,7 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
   STA_GEMM_CASE(128, A_CONV3, EPI_BF16)
   STA_GEMM_CASE(128, A_CONV3, EPI_HEAD)
 #undef STA_GEMM_CASE
-#undef STA_GEMM_CASE2
+#undef STA_GEMM_CASE3
   set_last_error("launch_gemm: unsupported (BN, amode, epilogue) combination");
   return 2;
 }

@@ -55,13 +55,17 @@ struct GemmParams {
   const float* head_b;  // [4]
   float* pts3d;         // [pixels][3]
   float* conf;          // [pixels]
+  int c_reduce;         // TMA epilogue, EPI_F32: out += result (in-place fp32 residual stream) via bulk reduce-add
   long long* dbg;       // optional clock64 trace (env STA_GEMM_TRACE), else null
 };
 
 // CG = 1: one CTA per 128 x BN tile (tcgen05 cta_group::1).
 // CG = 2: a CTA pair (cluster of 2 on one TPC) per 256 x BN tile (cta_group::2): each CTA stages its own
 //         128 rows of A and BN/2 rows of B, so per-SM shared-memory traffic per MMA is halved for B.
-template <int BN, int CG, int EW>
+// TMA = true: the epilogue writes through shared memory + TMA tensor stores (epilogue_tile_tma), else the
+// transposing per-warp staging path (epilogue_tile).
+constexpr int kRopeLd = 36;  // floats per staged sin/cos table row (32 + 4 pad: conflict-free row-per-lane reads)
+template <int BN, int CG, int EW, int EPI, bool TMA>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;
@@ -70,19 +74,26 @@ struct GemmCfg {
   static constexpr uint32_t BAR_BYTES = 256;
   static constexpr int EPI_WARPS = EW;  // 8 (mainloop-bound launches) or 16 (epilogue-heavy: 4 warps per scheduler)
   static constexpr int PARTS = EW / 4;  // column parts of a tile, one per epilogue warp of a lane quarter
-  static constexpr uint32_t EPI_SMEM_BYTES = 3 * 128 * 4 * sizeof(float);  // EPI_HEAD partial sums of parts 1..
-  static constexpr uint32_t STG_BYTES = EPI_WARPS * 32 * 36 * sizeof(float);  // per-warp [32][36] fp32 staging
-  static constexpr int ROPE_SMEM_ROWS = 64;                            // positions -1 .. 62
-  static constexpr uint32_t ROPE_SMEM_BYTES = ROPE_SMEM_ROWS * 32 * sizeof(float);
+  static constexpr uint32_t EPI_SMEM_BYTES = (EPI == EPI_HEAD) ? 3 * 128 * 4 * sizeof(float) : 0;  // partial sums
+  // per-warp staging: [32][36] fp32 transpose buffer, or one 4 KB SWIZZLE_128B box for the TMA store
+  static constexpr uint32_t STG_WARP_BYTES = TMA ? 4096 : 32 * 36 * sizeof(float);
+  static constexpr uint32_t STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
+  static constexpr int ROPE_SMEM_ROWS = 64;  // positions -1 .. 62
+  static constexpr uint32_t ROPE_SMEM_BYTES = (EPI == EPI_ROPE) ? ROPE_SMEM_ROWS * kRopeLd * sizeof(float) : 0;
   static constexpr uint32_t MAX_SMEM = 227 * 1024;
   static constexpr int STAGES_FIT =
       (MAX_SMEM - BAR_BYTES - EPI_SMEM_BYTES - STG_BYTES - ROPE_SMEM_BYTES) / (A_BYTES + B_BYTES);
-  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;  // 3 / 4 (CG=1), 4 / 6 (CG=2)
-  static constexpr uint32_t SMEM_BYTES =
-      STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + EPI_SMEM_BYTES + STG_BYTES + ROPE_SMEM_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  // layout: operand ring | staging (1024-byte aligned) | barriers | EPI_HEAD partials | RoPE table
+  static constexpr uint32_t OFF_STG = STAGES * (A_BYTES + B_BYTES);
+  static constexpr uint32_t OFF_BAR = OFF_STG + STG_BYTES;
+  static constexpr uint32_t OFF_EPI = OFF_BAR + BAR_BYTES;
+  static constexpr uint32_t OFF_ROPE = OFF_EPI + EPI_SMEM_BYTES;
+  static constexpr uint32_t SMEM_BYTES = OFF_ROPE + ROPE_SMEM_BYTES;
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int EPI_THREADS = 32 * EPI_WARPS;
-  static_assert(STAGES <= 8, "barrier area holds at most 8 stages");
+  static_assert(STAGES <= 8 && STAGES >= 3, "barrier area holds at most 8 stages");
+  static_assert(OFF_STG % 1024 == 0 && STG_WARP_BYTES % 16 == 0, "staging alignment");
 };
 
 // ---------------------------------------------------------------------------
@@ -318,7 +329,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
                                            __shfl_xor_sync(0xffffffffu, v.z, 4), __shfl_xor_sync(0xffffffffu, v.w, 4));
               const int pz = ((col >> 5) & 1) ? pos_x[it] : pos_y[it];
               const int ps = min(pz + 1, p.rope_smem_rows - 1);  // clamped shared-memory row (always safe to read)
-              const float4* tb = reinterpret_cast<const float4*>(rope_s + ps * 32) + ((cc & 15) >> 1);
+              const float4* tb = reinterpret_cast<const float4*>(rope_s + ps * kRopeLd) + ((cc & 15) >> 1);
               float4 t0 = tb[0];  // (cos f, sin f, cos f+1, sin f+1)
               float4 t1 = tb[1];  // (cos f+2, sin f+2, cos f+3, sin f+3)
               if (pz + 1 >= p.rope_smem_rows) {  // beyond the staged rows (very large images): global table
@@ -400,10 +411,163 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
   }
 }
 
-template <int BN, int AMODE, int EPI, int CG, int EW>
-__global__ void __launch_bounds__(GemmCfg<BN, CG, EW>::THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG, EW>;
+// ---------------------------------------------------------------------------
+// TMA-store epilogue for the wide linear layers (BN = 256; EPI_BF16 / EPI_GELU / EPI_ROPE / EPI_F32).
+//
+// The math stays in the tcgen05.ld mapping -- one accumulator ROW per thread, 32 consecutive columns per load --
+// so bias, GELU and the RoPE rotation (whose (i, i+16) partners sit in the same thread) need no shuffles.  The
+// results go to a per-warp 32-row x 128-byte shared-memory box in the SWIZZLE_128B layout (conflict-free 16-byte
+// stores) and leave with ONE bulk tensor store per box issued by lane 0: no per-lane global stores, rows >= M are
+// clipped by the tensor map, and the in-place fp32 residual stream (x += proj(..)) becomes a bulk reduce-add
+// performed by the L2, so the epilogue never loads the residual.  The TMEM load of chunk c+1 is in flight while
+// chunk c is processed, and the accumulator stage is released as soon as the last load has landed.
+// ---------------------------------------------------------------------------
+template <int BN, int EPI, int EW, typename Release>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmC, uint32_t taddr, int m_tile,
+                                                  int n_tile, int quarter, int part, uint8_t* cbuf, const float* rope_s,
+                                                  uint64_t* tfull_bar, uint32_t tfull_phase, Release&& release,
+                                                  long long* trace) {
+  constexpr int PARTS = EW / 4;
+  constexpr int CH = BN / PARTS;  // columns per epilogue warp
+  constexpr int NCH = CH / 32;    // 32-column TMEM loads per tile
+  // 8 warps (168 registers): the next chunk's TMEM load is in flight while the current one is processed;
+  // 16 warps (96 registers) rely on the four warps per scheduler instead
+  constexpr bool PF = (EW == 8);
+  constexpr bool OUT_F32 = (EPI == EPI_F32);
+  const int lane = threadIdx.x & 31;
+  const int colbase = n_tile * BN + part * CH;
+  const int row0 = m_tile * 128 + quarter * 32;
+  const uint32_t cb = smem_u32(cbuf);
+  const uint32_t srow = cb + lane * 128;  // this thread's row inside the box
+  const uint32_t sx = lane & 7;           // 128B swizzle: 16-byte chunk j lives at j ^ (row & 7)
+
+  [[maybe_unused]] int py = 0, px = 0;
+  if constexpr (EPI == EPI_ROPE) {
+    if (row0 + lane < p.M) {
+      const int2 pp = *reinterpret_cast<const int2*>(p.pos + 2 * static_cast<long long>(row0 + lane));
+      py = pp.x;
+      px = pp.y;
+      if (py < -1 || py > p.rope_max_pos || px < -1 || px > p.rope_max_pos)
+        device_fatal("token position outside the RoPE table");
+    }
+  }
+
+  // bias of chunk c is loaded one chunk ahead (warp-uniform addresses: L1 broadcast), so its latency never sits
+  // between the TMEM load and the math
+  float4 bcur[8];
+  const bool has_bias = p.bias != nullptr;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    bcur[j] = has_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + colbase) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+  mbar_wait(tfull_bar, tfull_phase);
+  tc_fence_after();
+  if (trace) trace[0] = clock64();
+  uint32_t acc[PF ? 2 : 1][32];
+  tmem_ld32(taddr, acc[0]);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    tmem_ld_wait();
+    float* v = reinterpret_cast<float*>(acc[PF ? (c & 1) : 0]);
+    const int col = colbase + c * 32;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j] += bcur[j].x; v[4 * j + 1] += bcur[j].y; v[4 * j + 2] += bcur[j].z; v[4 * j + 3] += bcur[j].w;
+    }
+    if (c + 1 < NCH) {
+      if constexpr (PF) tmem_ld32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
+      if (has_bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bcur[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col + 32) + j);
+      }
+    } else {
+      release();
+    }
+    if (trace) trace[1 + 3 * c] = clock64();
+    if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    }
+    if constexpr (EPI == EPI_BF16) {
+      if (p.relu_main) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+      }
+    }
+    if constexpr (EPI == EPI_ROPE) {
+      // 2-D RoPE (pos_embed/pos_embed.py:149-185, curope/kernels.cu:17-82): a 32-column chunk is one half of a
+      // 64-wide head -- the y-half (rotated by pos_y) or the x-half (pos_x); inside it the pairs are (i, i + 16).
+      if (col < p.rope_cols) {  // warp-uniform: the V columns are not rotated
+        const int ps = (((col >> 5) & 1) ? px : py) + 1;
+        const float4* tb = (ps < p.rope_smem_rows)
+                               ? reinterpret_cast<const float4*>(rope_s + ps * kRopeLd)
+                               : reinterpret_cast<const float4*>(p.rope_tab + static_cast<long long>(ps) * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = tb[j];  // (cos f, sin f, cos f+1, sin f+1), f = 2j
+          const float a0 = v[2 * j], b0 = v[2 * j + 16], a1 = v[2 * j + 1], b1 = v[2 * j + 17];
+          v[2 * j] = fmaf(-b0, t.y, a0 * t.x);
+          v[2 * j + 16] = fmaf(a0, t.y, b0 * t.x);
+          v[2 * j + 1] = fmaf(-b1, t.w, a1 * t.z);
+          v[2 * j + 17] = fmaf(a1, t.w, b1 * t.z);
+        }
+      }
+    }
+    if (trace) trace[2 + 3 * c] = clock64();
+    // ---- registers -> swizzled box -> bulk tensor store ----
+    if constexpr (OUT_F32) {
+      // one box per chunk: 32 rows x 32 fp32 columns
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ sx) << 4)), "f"(v[4 * j]),
+                     "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                     : "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (p.c_reduce) tma_reduce_add_2d(tmC, cbuf, col, row0);
+        else tma_store_2d(tmC, cbuf, col, row0);
+        tma_store_commit();
+      }
+    } else {
+      // one box per two chunks: 32 rows x 64 bf16 columns
+      const int sub = c & 1;
+      if (sub == 0) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((sub * 4 + j) ^ sx) << 4)),
+                     "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])), "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
+                     "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+                     : "memory");
+      if (sub == 1) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmC, cbuf, col - 32, row0);
+          tma_store_commit();
+        }
+      }
+    }
+    if constexpr (!PF) {
+      if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, acc[0]);  // the registers are free again
+    }
+    if (trace) trace[3 + 3 * c] = clock64();
+  }
+}
+
+template <int BN, int AMODE, int EPI, int CG, int EW, bool TMA>
+__global__ void __launch_bounds__(GemmCfg<BN, CG, EW, EPI, TMA>::THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  using Cfg = GemmCfg<BN, CG, EW, EPI, TMA>;
+  static_assert(!TMA || (AMODE == A_LINEAR && BN == 256 &&
+                         (EPI == EPI_BF16 || EPI == EPI_GELU || EPI == EPI_F32 || EPI == EPI_ROPE)),
+                "TMA-store epilogue: wide linear layers only");
   constexpr int STAGES = Cfg::STAGES;
   constexpr uint32_t A_BYTES = Cfg::A_BYTES;
   constexpr uint32_t B_BYTES = Cfg::B_BYTES;
@@ -411,15 +575,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * (A_BYTES + B_BYTES) + Cfg::BAR_BYTES);
-  float* stg_all = reinterpret_cast<float*>(smem + STAGES * (A_BYTES + B_BYTES) + Cfg::BAR_BYTES + Cfg::EPI_SMEM_BYTES);
-  float* rope_s = stg_all + Cfg::EPI_WARPS * kStageFloatsPerWarp;
+  [[maybe_unused]] float* epi_smem = reinterpret_cast<float*>(smem + Cfg::OFF_EPI);
+  uint8_t* stg_all = smem + Cfg::OFF_STG;
+  [[maybe_unused]] float* rope_s = reinterpret_cast<float*>(smem + Cfg::OFF_ROPE);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -451,6 +615,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (TMA) tma_prefetch_desc(&tmC);
   }
   if constexpr (EPI == EPI_ROPE) {
     // the sin/cos table is a constant of the library (not produced by the previous kernel): stage the rows for
@@ -458,7 +623,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp >= 4) {
       const int nfl = p.rope_smem_rows * 32;
       for (int i = (threadIdx.x - 128) * 4; i < nfl; i += Cfg::EPI_THREADS * 4)
-        *reinterpret_cast<float4*>(rope_s + i) = __ldg(reinterpret_cast<const float4*>(p.rope_tab + i));
+        *reinterpret_cast<float4*>(rope_s + (i >> 5) * kRopeLd + (i & 31)) =
+            __ldg(reinterpret_cast<const float4*>(p.rope_tab + i));
     }
   }
   if (warp == 2) {
@@ -573,16 +739,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (trc) p.dbg[4 * tcount + 0] = clock64();
       if (trc) p.dbg[4 * tcount + 1] = clock64();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + part * (BN / Cfg::PARTS);
-      epilogue_tile<BN, AMODE, EPI, EW>(p, taddr, m_tile, n_tile, quarter, part, epi_smem,
-                                    stg_all + (warp - 4) * kStageFloatsPerWarp, rope_s, &tfull[acc], acc_phase);
-      if (trc) p.dbg[4 * tcount + 2] = clock64();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 1 || leader) mbar_arrive(&tempty[acc]); else mbar_arrive_remote(&tempty[acc], 0);
+      // hand the accumulator stage back to the MMA warp (called once all of this warp's TMEM loads have landed)
+      auto release = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 1 || leader) mbar_arrive(&tempty[acc]); else mbar_arrive_remote(&tempty[acc], 0);
+        }
+      };
+      if constexpr (TMA) {
+        epilogue_tile_tma<BN, EPI, EW>(p, &tmC, taddr, m_tile, n_tile, quarter, part,
+                                       stg_all + (warp - 4) * Cfg::STG_WARP_BYTES, rope_s, &tfull[acc], acc_phase, release,
+                                       (trc && tcount < 16) ? p.dbg + 512 + 16 * tcount : nullptr);
+      } else {
+        epilogue_tile<BN, AMODE, EPI, EW>(p, taddr, m_tile, n_tile, quarter, part, epi_smem,
+                                          reinterpret_cast<float*>(stg_all + (warp - 4) * Cfg::STG_WARP_BYTES), rope_s,
+                                          &tfull[acc], acc_phase);
+        release();
       }
+      if (trc) p.dbg[4 * tcount + 2] = clock64();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if constexpr (TMA) {
+      if (lane == 0) tma_store_wait_all();  // the bulk stores read this CTA's shared memory
     }
   }
 
