@@ -155,6 +155,22 @@ int sta_op_cast_f32_bf16(const float* in, void* out_bf16, int64_t rows, int C, i
  * curope.rope_2d (pos_embed/curope/curope.cpp:49-65, kernels.cu:84-108), base 100, F0 = 1. */
 int sta_op_rope2d(void* tokens_bf16, const int64_t* pos, int B, int N, int H, void* stream);
 
+
+/* ---- pointmap consumers: what OnlineSLAM.regress_two_views / connect_view_i_j compute from
+ * the head outputs right after the boundary.  Device pointers, fp32; `scratch` is a caller-owned device buffer of
+ * sta_pointmap_scratch_bytes(V) bytes (8-byte aligned).  No host synchronisation. ---- */
+size_t sta_pointmap_scratch_bytes(int V);
+/* estimate_intrinsic_from_pts3d (vista_slam/utils/slam_utils.py:8-79, call site slam.py:184) fused with
+ * depths = pts3d[..., 2] (slam.py:185) and conf.mean() per view (pose_graph.py:41).
+ * pts3d [V][H][W][3], conf [V][H][W]; shared != 0 -> K_out [3][3], else [V][3][3];
+ * depth_out [V][H][W] and conf_mean_out [V] may be NULL. */
+int sta_pointmap_consumers(const float* pts3d, const float* conf, int V, int H, int W, int shared, float* K_out,
+                           float* depth_out, float* conf_mean_out, void* scratch, void* stream);
+/* estimate_scale_with_depth_and_confidence (slam_utils.py:168-190, call site slam.py:224) and
+ * scale_conf = (ci * cj).sqrt().mean() (slam.py:227): out2 = {scale, scale_conf}; n elements per map. */
+int sta_depth_scale(const float* Di, const float* Dj, const float* ci, const float* cj, int64_t n, float* out2,
+                    void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,7 +42,7 @@ def test_implicit_gemm_conv_and_head(capsys):
 
 
 def test_attention_self_and_cross(capsys):
-    assert len(_collect(bu.group_attention, capsys)) == 10
+    assert len(_collect(bu.group_attention, capsys)) == 11
 
 
 def test_bandwidth_kernels(capsys):

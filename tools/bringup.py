@@ -212,7 +212,7 @@ def group_attention():
     L = lib()
     for (batch, heads, n, shift, split) in [(2, 3, 128, 0, 0), (2, 3, 196, 0, 0), (2, 12, 769, 0, 0), (4, 12, 769, 2, 0),
                                             (3, 16, 768, 0, 0), (4, 12, 769, 2, 1), (2, 12, 197, 0, 1), (2, 3, 130, 0, 1),
-                                            (2, 3, 257, 1, 1), (3, 2, 1, 0, 1)]:
+                                            (2, 3, 257, 1, 1), (3, 2, 1, 0, 1), (2, 2, 901, 1, 1)]:
         C = heads * 64
         qkv = torch.randn(batch, n, 3 * C, device=dev).bfloat16()
         out = torch.zeros(batch, n, C, device=dev, dtype=torch.bfloat16)
@@ -347,6 +347,22 @@ def group_perf():
                                                      ptr(out), C, batch, heads, n, n, 0, 0.125, split, cur_stream())))
         fl = 4.0 * batch * heads * n * n * 64
         print("attention b%d h%d n%d split%d: %.3f ms = %.0f TFLOP/s" % (batch, heads, n, split, ms, fl / ms / 1e9), flush=True)
+    # bandwidth kernels at the cfg-2 sizes (16 images per DPT pass, 32 images in the trunk)
+    for (nimg, H, W, C) in [(16, 192, 256, 128), (16, 96, 128, 256), (16, 48, 64, 256)]:
+        x = torch.randn(nimg, H, W, C, device=dev).bfloat16()
+        o = torch.zeros(nimg, 2 * H, 2 * W, C, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda: check(L.sta_op_upsample2x(ptr(x), ptr(o), nimg, H, W, C, cur_stream())))
+        gb = (x.numel() + o.numel()) * 2 / 1e9
+        print("upsample2x %dx%dx%dx%d: %.3f ms = %.0f GB/s" % (nimg, H, W, C, ms, gb / ms * 1e3), flush=True)
+    for (rows, C) in [(24576, 1024), (24608, 768)]:
+        x = torch.randn(rows, C, device=dev)
+        g = torch.randn(C, device=dev)
+        b = torch.randn(C, device=dev)
+        o = torch.zeros(rows, C, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda: check(L.sta_op_layernorm(ptr(x), rows, C, 1e-6, ptr(g), ptr(b), ptr(o), None, None, None, 0,
+                                                     cur_stream())))
+        gb = rows * C * 6 / 1e9
+        print("layernorm %dx%d: %.3f ms = %.0f GB/s" % (rows, C, ms, gb / ms * 1e3), flush=True)
 
 
 def main():

@@ -76,6 +76,10 @@ def lib():
     L.sta_op_im2col_3x3_s2.argtypes = [vp, vp, i, i, i, i, vp]
     L.sta_op_cast_f32_bf16.argtypes = [vp, vp, i64, i, i, vp]
     L.sta_op_rope2d.argtypes = [vp, vp, i, i, i, vp]
+    L.sta_pointmap_scratch_bytes.argtypes = [i]
+    L.sta_pointmap_scratch_bytes.restype = ctypes.c_size_t
+    L.sta_pointmap_consumers.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
+    L.sta_depth_scale.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
     _lib = L
     return L
 

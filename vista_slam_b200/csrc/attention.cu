@@ -436,42 +436,58 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 // ---------------------------------------------------------------------------
 // Query row 0 of every (sample, head) -- the decoder's pose token -- against all nk keys.
-// One CTA (256 threads) per (head, sample): scores -> shared memory, block max / sum, then the
-// 64 output features as coalesced column sums over V.  ~1e-4 of the attention FLOPs.
+// One CTA (256 threads) per (head, sample): scores -> shared memory, block max / sum, then P V with 16-byte
+// loads.  ~1e-4 of the attention FLOPs but latency-bound: the loads are batched so that the whole kernel is
+// about five DRAM round trips.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 attention_row0_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, int q_col0, const __nv_bfloat16* __restrict__ k,
                       long long ldk, int k_col0, const __nv_bfloat16* __restrict__ v, long long ldv, int v_col0,
                       __nv_bfloat16* __restrict__ out, long long ldo, int nq, int nk, int batch, int kv_batch_shift,
                       float scale_log2) {
-  extern __shared__ float sc[];  // nk scores | 16 floats of reduction scratch | 256 partial outputs
+  extern __shared__ float sc[];  // nk scores | 16 floats of reduction scratch | 32 x 64 partial outputs
   float* red = sc + ((nk + 3) & ~3);
   __shared__ float qs[64];
   pdl_wait();
   pdl_launch_dependents();
-  const int head = blockIdx.x, b = blockIdx.y;
+  // last samples first: their K / V rows are the most recent (still L2-resident) reads of the tiled kernel
+  const int head = blockIdx.x, b = static_cast<int>(gridDim.y) - 1 - static_cast<int>(blockIdx.y);
   const int kvb = (b + kv_batch_shift) % batch;
   const int tid = threadIdx.x;
   if (tid < 64) qs[tid] = __bfloat162float(q[static_cast<long long>(b) * nq * ldq + q_col0 + head * 64 + tid]);
   __syncthreads();
-  // ---- scores: one key per thread per round (8 x 16-byte loads in flight per key) ----
+  // ---- scores: two keys per thread per round (16 x 16-byte loads in flight; 769 keys = 2 DRAM round trips) ----
   const __nv_bfloat16* kb = k + static_cast<long long>(kvb) * nk * ldk + k_col0 + head * 64;
   float mx = -INFINITY;
-  for (int j = tid; j < nk; j += 256) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kb + static_cast<long long>(j) * ldk);
-    uint4 w[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) w[c] = __ldg(kr + c);
-    float acc = 0.f;
+  for (int j0 = tid; j0 < nk; j0 += 512) {
+    const int j1 = j0 + 256;
+    const bool has1 = j1 < nk;
+    const uint4* kr0 = reinterpret_cast<const uint4*>(kb + static_cast<long long>(j0) * ldk);
+    const uint4* kr1 = reinterpret_cast<const uint4*>(kb + static_cast<long long>(has1 ? j1 : j0) * ldk);
+    uint4 w0[8], w1[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      acc += qs[8 * c + 0] * bf16_lo(w[c].x) + qs[8 * c + 1] * bf16_hi(w[c].x) + qs[8 * c + 2] * bf16_lo(w[c].y) +
-             qs[8 * c + 3] * bf16_hi(w[c].y) + qs[8 * c + 4] * bf16_lo(w[c].z) + qs[8 * c + 5] * bf16_hi(w[c].z) +
-             qs[8 * c + 6] * bf16_lo(w[c].w) + qs[8 * c + 7] * bf16_hi(w[c].w);
+      w0[c] = __ldg(kr0 + c);
+      w1[c] = __ldg(kr1 + c);
     }
-    acc *= scale_log2;
-    sc[j] = acc;
-    mx = fmaxf(mx, acc);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 qa = *reinterpret_cast<const float4*>(qs + 8 * c);
+      const float4 qb = *reinterpret_cast<const float4*>(qs + 8 * c + 4);
+      a0 += qa.x * bf16_lo(w0[c].x) + qa.y * bf16_hi(w0[c].x) + qa.z * bf16_lo(w0[c].y) + qa.w * bf16_hi(w0[c].y) +
+            qb.x * bf16_lo(w0[c].z) + qb.y * bf16_hi(w0[c].z) + qb.z * bf16_lo(w0[c].w) + qb.w * bf16_hi(w0[c].w);
+      a1 += qa.x * bf16_lo(w1[c].x) + qa.y * bf16_hi(w1[c].x) + qa.z * bf16_lo(w1[c].y) + qa.w * bf16_hi(w1[c].y) +
+            qb.x * bf16_lo(w1[c].z) + qb.y * bf16_hi(w1[c].z) + qb.z * bf16_lo(w1[c].w) + qb.w * bf16_hi(w1[c].w);
+    }
+    a0 *= scale_log2;
+    sc[j0] = a0;
+    mx = fmaxf(mx, a0);
+    if (has1) {
+      a1 *= scale_log2;
+      sc[j1] = a1;
+      mx = fmaxf(mx, a1);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -494,25 +510,38 @@ attention_row0_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, int q_
   sum = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) sum += red[8 + i];
-  // ---- output feature d = tid & 63; the 4 quarter-blocks take keys j = g (mod 4); 8 independent loads in flight ----
-  const int d = tid & 63, g = tid >> 6;
-  const __nv_bfloat16* vb = v + static_cast<long long>(kvb) * nk * ldv + v_col0 + head * 64 + d;
-  float o = 0.f;
-  int j = g;
-  for (; j + 28 < nk; j += 32) {
-    float vv[8];
+  // ---- P V: thread (kg = tid / 8, fg = tid % 8) owns keys kg, kg + 32, ... and 8 features (one 16-byte load per
+  //      key, 13 in flight), then the 32 key groups are combined through shared memory ----
+  const int fg = tid & 7, kg = tid >> 3;
+  const __nv_bfloat16* vb = v + static_cast<long long>(kvb) * nk * ldv + v_col0 + head * 64 + 8 * fg;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j = kg; j < nk; j += 32 * 13) {
+    uint4 w[13];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) vv[u] = __bfloat162float(vb[static_cast<long long>(j + 4 * u) * ldv]);
+    for (int u = 0; u < 13; ++u) {
+      const int jj = j + 32 * u;
+      w[u] = (jj < nk) ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(jj) * ldv)) : make_uint4(0u, 0u, 0u, 0u);
+    }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) o = fmaf(sc[j + 4 * u], vv[u], o);
+    for (int u = 0; u < 13; ++u) {
+      const int jj = j + 32 * u;
+      const float pj = (jj < nk) ? sc[jj] : 0.f;
+      acc[0] = fmaf(pj, bf16_lo(w[u].x), acc[0]); acc[1] = fmaf(pj, bf16_hi(w[u].x), acc[1]);
+      acc[2] = fmaf(pj, bf16_lo(w[u].y), acc[2]); acc[3] = fmaf(pj, bf16_hi(w[u].y), acc[3]);
+      acc[4] = fmaf(pj, bf16_lo(w[u].z), acc[4]); acc[5] = fmaf(pj, bf16_hi(w[u].z), acc[5]);
+      acc[6] = fmaf(pj, bf16_lo(w[u].w), acc[6]); acc[7] = fmaf(pj, bf16_hi(w[u].w), acc[7]);
+    }
   }
-  for (; j < nk; j += 4) o = fmaf(sc[j], __bfloat162float(vb[static_cast<long long>(j) * ldv]), o);
-  float* part = red + 16;
-  part[tid] = o;
+  float* part = red + 16;  // [32 key groups][64 features]
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[kg * 64 + 8 * fg + i] = acc[i];
   __syncthreads();
-  if (tid < 64)
-    out[static_cast<long long>(b) * nq * ldo + head * 64 + tid] =
-        __float2bfloat16(((part[tid] + part[tid + 64]) + (part[tid + 128] + part[tid + 192])) / sum);
+  if (tid < 64) {
+    float o = 0.f;
+#pragma unroll
+    for (int g = 0; g < 32; ++g) o += part[g * 64 + tid];
+    out[static_cast<long long>(b) * nq * ldo + head * 64 + tid] = __float2bfloat16(o / sum);
+  }
 }
 
 int make_qkv_map(CUtensorMap* m, const bf16* base, long long ld, int ntok, int batch) {
@@ -549,12 +578,13 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   p.out = a.out;
   p.ldo = a.ldo;
   p.heads = a.heads;
-  const int split = (a.split_first_row && a.nq > 1) ? 1 : 0;
+  const size_t row0_smem = (((a.nk + 3) & ~3) + 16 + 32 * 64) * sizeof(float);
+  const int split = (a.split_first_row && a.nq > 1 && row0_smem <= 48 * 1024) ? 1 : 0;
   p.q_row0 = split;
   p.qpairs = (a.nq - split + 255) / 256;
   p.nitems = p.qpairs * a.heads * a.batch;
   if (split) {
-    const size_t smem = (((a.nk + 3) & ~3) + 16 + 256) * sizeof(float);
+    const size_t smem = row0_smem;
     STA_CHECK_CUDA(launch_pdl(attention_row0_kernel, dim3(a.heads, a.batch), dim3(256), smem, stream, 1, a.q, a.ldq, a.q_col0, a.k,
                               a.ldk, a.k_col0, a.v, a.ldv, a.v_col0, a.out, a.ldo, a.nq, a.nk, a.batch, a.kv_batch_shift,
                               p.scale_log2));

@@ -269,8 +269,10 @@ int launch_copy_f32(const float* in, float* out, long long n, cudaStream_t strea
 // bilinear x2 upsampling, align_corners=True, NHWC bf16 (dpt_block.py:215-216,320).
 // src coordinate = dst * (in - 1) / (out - 1); weights in fp32 like ATen's
 // upsample_bilinear2d (area_pixel_compute_scale with align_corners).
-// One thread: one output pixel x 8 channels.
+// One block: one output row (blockIdx.y) of one image (blockIdx.z), a run of kUpsPix * (256 / (C/8)) pixels; one
+// thread: 8 channels of kUpsPix pixels, so the row weights are computed once and all index math is 32-bit.
 // ---------------------------------------------------------------------------
+constexpr int kUpsPix = 4;
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int nimg, int H, int W, int C,
                   int OH, int OW) {
@@ -278,47 +280,62 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restric
   pdl_launch_dependents();
   // the interpolation grid is always the full 2H x 2W one; (OH, OW) <= (2H, 2W) only crops the output
   const int FH = 2 * H, FW = 2 * W;
-  const int cpp = C / 8;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(nimg) * OH * OW * cpp;
-  if (idx >= total) return;
-  const int ch = static_cast<int>(idx % cpp);
-  long long pix = idx / cpp;
-  const int ox = static_cast<int>(pix % OW);
-  pix /= OW;
-  const int oy = static_cast<int>(pix % OH);
-  const int n = static_cast<int>(pix / OH);
+  const int cpp = C >> 3;            // 16-byte channel groups per pixel
+  const int ppb = 256 / cpp;         // pixels per block pass
+  const int ch = threadIdx.x % cpp;
+  const int pl = threadIdx.x / cpp;
+  if (pl >= ppb) return;
+  const int oy = blockIdx.y, n = blockIdx.z;
   const float sy = (FH > 1) ? static_cast<float>(H - 1) / static_cast<float>(FH - 1) : 0.f;
   const float sx = (FW > 1) ? static_cast<float>(W - 1) / static_cast<float>(FW - 1) : 0.f;
-  const float fy = sy * oy, fx = sx * ox;
-  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
-  const float ly = fy - y0, lx = fx - x0;
-  const float hy = 1.f - ly, hx = 1.f - lx;
-  const __nv_bfloat16* base = in + static_cast<long long>(n) * H * W * C + ch * 8;
-  const uint4 q00 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * W + x0) * C);
-  const uint4 q01 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * W + x1) * C);
-  const uint4 q10 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * W + x0) * C);
-  const uint4 q11 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * W + x1) * C);
-  const uint32_t a00[4] = {q00.x, q00.y, q00.z, q00.w}, a01[4] = {q01.x, q01.y, q01.z, q01.w};
-  const uint32_t a10[4] = {q10.x, q10.y, q10.z, q10.w}, a11[4] = {q11.x, q11.y, q11.z, q11.w};
-  uint32_t r[4];
+  const float fy = sy * oy;
+  const int y0 = static_cast<int>(fy);
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
+  const float ly = fy - y0, hy = 1.f - ly;
+  const __nv_bfloat16* row0 = in + (static_cast<long long>(n) * H + y0) * W * C + ch * 8;
+  const __nv_bfloat16* row1 = in + (static_cast<long long>(n) * H + y1) * W * C + ch * 8;
+  __nv_bfloat16* orow = out + (static_cast<long long>(n) * OH + oy) * OW * C + ch * 8;
+  const int ox_base = blockIdx.x * (ppb * kUpsPix) + pl;
+  uint4 q00[kUpsPix], q01[kUpsPix], q10[kUpsPix], q11[kUpsPix];
+  float lxs[kUpsPix];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float lo = hy * (hx * bf16_lo(a00[i]) + lx * bf16_lo(a01[i])) + ly * (hx * bf16_lo(a10[i]) + lx * bf16_lo(a11[i]));
-    const float hi = hy * (hx * bf16_hi(a00[i]) + lx * bf16_hi(a01[i])) + ly * (hx * bf16_hi(a10[i]) + lx * bf16_hi(a11[i]));
-    r[i] = pack_bf16x2(lo, hi);
+  for (int k = 0; k < kUpsPix; ++k) {
+    const int ox = ox_base + k * ppb;
+    const float fx = sx * ox;
+    int x0 = static_cast<int>(fx);
+    x0 = x0 < W - 1 ? x0 : W - 1;  // also keeps the loads of out-of-range pixels (ox >= OW) in bounds
+    const int x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    lxs[k] = fx - x0;
+    q00[k] = *reinterpret_cast<const uint4*>(row0 + x0 * C);
+    q01[k] = *reinterpret_cast<const uint4*>(row0 + x1 * C);
+    q10[k] = *reinterpret_cast<const uint4*>(row1 + x0 * C);
+    q11[k] = *reinterpret_cast<const uint4*>(row1 + x1 * C);
   }
-  *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * OH + oy) * OW + ox) * C + ch * 8) =
-      make_uint4(r[0], r[1], r[2], r[3]);
+#pragma unroll
+  for (int k = 0; k < kUpsPix; ++k) {
+    const int ox = ox_base + k * ppb;
+    if (ox >= OW) break;
+    const float lx = lxs[k], hx = 1.f - lx;
+    const uint32_t a00[4] = {q00[k].x, q00[k].y, q00[k].z, q00[k].w}, a01[4] = {q01[k].x, q01[k].y, q01[k].z, q01[k].w};
+    const uint32_t a10[4] = {q10[k].x, q10[k].y, q10[k].z, q10[k].w}, a11[4] = {q11[k].x, q11[k].y, q11[k].z, q11[k].w};
+    uint32_t r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float lo = hy * (hx * bf16_lo(a00[i]) + lx * bf16_lo(a01[i])) + ly * (hx * bf16_lo(a10[i]) + lx * bf16_lo(a11[i]));
+      const float hi = hy * (hx * bf16_hi(a00[i]) + lx * bf16_hi(a01[i])) + ly * (hx * bf16_hi(a10[i]) + lx * bf16_hi(a11[i]));
+      r[i] = pack_bf16x2(lo, hi);
+    }
+    *reinterpret_cast<uint4*>(orow + static_cast<long long>(ox) * C) = make_uint4(r[0], r[1], r[2], r[3]);
+  }
 }
 int launch_upsample2x(const bf16* in, bf16* out, int nimg, int H, int W, int C, int OH, int OW, cudaStream_t stream) {
-  STA_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+  STA_REQUIRE(C % 8 == 0 && C / 8 <= 256, "C must be a multiple of 8, at most 2048");
   STA_REQUIRE(OH <= 2 * H && OW <= 2 * W && OH > 0 && OW > 0, "output crop must fit inside the 2x grid");
-  const long long total = static_cast<long long>(nimg) * OH * OW * (C / 8);
-  if (total == 0) return 0;
-  STA_CHECK_CUDA(launch_pdl(upsample2x_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, stream, 1, in, out, nimg, H,
-                            W, C, OH, OW));
+  STA_REQUIRE(OH <= 65535 && nimg <= 65535, "grid limits");
+  if (nimg == 0) return 0;
+  const int ppb = 256 / (C / 8);
+  const int gx = (OW + ppb * kUpsPix - 1) / (ppb * kUpsPix);
+  STA_CHECK_CUDA(launch_pdl(upsample2x_kernel, dim3(gx, OH, nimg), dim3(256), 0, stream, 1, in, out, nimg, H, W, C, OH, OW));
   STA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -54,6 +54,12 @@ int launch_fill_pose_token(float* x, const float* tok, int samples, int tokens_p
                            cudaStream_t stream);
 int launch_upsample2x(const bf16* in, bf16* out, int nimg, int H, int W, int C, int OH, int OW, cudaStream_t stream);
 int launch_rope2d(bf16* tokens, const long long* pos, int B, int N, int H, cudaStream_t stream);
+// pointmap.cu: reductions over the head outputs (slam_utils.py:8-79,168-190)
+size_t pointmap_scratch_bytes(int V);
+int launch_pointmap_consumers(const float* pts3d, const float* conf, int V, int H, int W, int shared, float* K_out,
+                              float* depth_out, float* conf_mean_out, void* scratch, cudaStream_t stream);
+int launch_depth_scale(const float* Di, const float* Dj, const float* ci, const float* cj, long long n, float* out2,
+                       void* scratch, cudaStream_t stream);
 int launch_im2col_3x3_s2(const bf16* in, bf16* out, int nimg, int H, int W, int C, cudaStream_t stream);
 int launch_copy_f32(const float* in, float* out, long long n, cudaStream_t stream);
 

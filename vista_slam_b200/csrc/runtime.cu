@@ -185,7 +185,7 @@ struct StaModel {
   size_t io_bytes = 0;
   static constexpr int kMaxHostChunks = 32;
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the host entry point
-  cudaEvent_t ev_in[kMaxHostChunks] = {}, ev_done[kMaxHostChunks] = {}, ev_start = nullptr;
+  cudaEvent_t ev_in[kMaxHostChunks] = {}, ev_done[kMaxHostChunks] = {}, ev_v1[kMaxHostChunks] = {}, ev_start = nullptr;
   int64_t launches = 0;
   int max_pairs_per_chunk = 16;
 
@@ -623,20 +623,30 @@ int run_decoder(const Ctx& c, int B, int N, DecBufs& d, float* const* out1, floa
   m->launches++;
   RUN(launch_fill_pose_token(d.xd, m->pose_tok, S, M, kDecDim, c.st));
   RUN(emit(0));
+  // the pose token (query row 0) goes to the attention kernel's spare warps when that saves a pair of query tiles
+  // The pose token (query row 0) can go to a separate small kernel so that the tiled kernel runs 3 instead of 4
+  // query-tile pairs per (head, sample).  Measured on B200 the attention time drops (7.9 -> 7.5 ms per cfg-2 step) but
+  // the 24 extra launches cost more than that end to end (34.0 vs 33.4 ms), so it is off unless STA_ATTN_SPLIT_POSE=1.
+  static int split_env = -1;
+  if (split_env < 0) {
+    const char* e = getenv("STA_ATTN_SPLIT_POSE");
+    split_env = (e && e[0] == '1') ? 1 : 0;
+  }
+  const int split_pose = (split_env && (M - 1 + 255) / 256 < (M + 255) / 256) ? 1 : 0;
   for (int l = 0; l < 12; ++l) {
     const DecBlock& b = m->dec[l];
     // self-attention on norm1(x); norm_y(x) is what the partner view cross-attends to
     RUN(ln(c, d.xd, Td, kDecDim, b.n1, d.ln1, &b.ny, d.lny));
     RUN(linear(c, EPI_ROPE, d.ln1, Td, b.qkv, d.qkv, nullptr, d.pos, 2 * kDecDim));
     RUN(attn(c, d.qkv, 3 * kDecDim, 0, d.qkv, 3 * kDecDim, kDecDim, d.qkv, 3 * kDecDim, 2 * kDecDim, d.att, kDecDim, S,
-             kDecHeads, M, M, 0, /*split_first_row=*/0));
+             kDecHeads, M, M, 0, split_pose));
     RUN(linear(c, EPI_F32, d.att, Td, b.proj, d.xd, d.xd));
     // cross-attention: q from norm2(x), k/v from norm_y(partner input) -- kv sample = (s + B) % 2B
     RUN(linear(c, EPI_ROPE, d.lny, Td, b.ckv, d.kvc, nullptr, d.pos, kDecDim));
     RUN(ln(c, d.xd, Td, kDecDim, b.n2, d.ln1));
     RUN(linear(c, EPI_ROPE, d.ln1, Td, b.cq, d.qc, nullptr, d.pos, kDecDim));
     RUN(attn(c, d.qc, kDecDim, 0, d.kvc, 2 * kDecDim, 0, d.kvc, 2 * kDecDim, kDecDim, d.att, kDecDim, S, kDecHeads, M, M,
-             B, /*split_first_row=*/0));
+             B, split_pose));
     RUN(linear(c, EPI_F32, d.att, Td, b.cproj, d.xd, d.xd));
     // MLP
     RUN(ln(c, d.xd, Td, kDecDim, b.n3, d.ln1));
@@ -785,7 +795,8 @@ int check_ready(StaModel* m) {
 }
 
 int forward_chunk(const Ctx& c, const void* img1, const void* img2, int img_is_bf16, int B, int H, int W,
-                  float* pts3d, float* conf, float* pose, float* pose_conf, int B_total) {
+                  float* pts3d, float* conf, float* pose, float* pose_conf, int B_total,
+                  cudaEvent_t ev_view1_done = nullptr) {
   StaModel* m = c.m;
   const int h = H / 16, w = W / 16, N = h * w, S = 2 * B, M = N + 1;
   RUN(ensure_ws(m, S, h, w));
@@ -820,6 +831,8 @@ int forward_chunk(const Ctx& c, const void* img1, const void* img2, int img_is_b
                 d.hook[2] + tok0 * 768, pts3d + static_cast<long long>(v) * B_total * px * 3,
                 conf + static_cast<long long>(v) * B_total * px));
     ws.off = save;
+    // view 1's pointmaps are final: the host entry point starts their D2H copy under view 2's head
+    if (v == 0 && ev_view1_done) STA_CHECK_CUDA(cudaEventRecord(ev_view1_done, c.st));
   }
   return 0;
 }
@@ -889,6 +902,7 @@ void sta_destroy(StaModel* m) {
     for (int i = 0; i < StaModel::kMaxHostChunks; ++i) {
       cudaEventDestroy(m->ev_in[i]);
       cudaEventDestroy(m->ev_done[i]);
+      cudaEventDestroy(m->ev_v1[i]);
     }
     cudaEventDestroy(m->ev_start);
   }
@@ -1149,6 +1163,7 @@ int sta_forward_pairs_host(StaModel* m, const void* img1_host, const void* img2_
     for (int i = 0; i < StaModel::kMaxHostChunks; ++i) {
       STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming));
       STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
+      STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_v1[i], cudaEventDisableTiming));
     }
     STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
   }
@@ -1190,15 +1205,18 @@ int sta_forward_pairs_host(StaModel* m, const void* img1_host, const void* img2_
     STA_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_in[c], 0));
     RUN(forward_chunk(cx, d_img1 + b0 * img_pair, d_img2 + b0 * img_pair, img_is_bf16, nb, H, W,
                       d_pts + static_cast<size_t>(b0) * px * 3, d_conf + static_cast<size_t>(b0) * px,
-                      d_pose + static_cast<size_t>(b0) * 16, d_pconf + b0, B));
+                      d_pose + static_cast<size_t>(b0) * 16, d_pconf + b0, B, m->ev_v1[c]));
     STA_CHECK_CUDA(cudaEventRecord(m->ev_done[c], st));
-    STA_CHECK_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_done[c], 0));
     for (int v = 0; v < 2; ++v) {
+      STA_CHECK_CUDA(cudaStreamWaitEvent(m->s_out, v == 0 ? m->ev_v1[c] : m->ev_done[c], 0));
       const size_t o = static_cast<size_t>(v) * B + b0;
       STA_CHECK_CUDA(cudaMemcpyAsync(pts3d_out_host + o * px * 3, d_pts + o * px * 3, nb * px * 3 * sizeof(float),
                                      cudaMemcpyDeviceToHost, m->s_out));
       STA_CHECK_CUDA(cudaMemcpyAsync(conf_out_host + o * px, d_conf + o * px, nb * px * sizeof(float),
                                      cudaMemcpyDeviceToHost, m->s_out));
+    }
+    for (int v = 0; v < 2; ++v) {
+      const size_t o = static_cast<size_t>(v) * B + b0;
       STA_CHECK_CUDA(cudaMemcpyAsync(pose_out_host + o * 16, d_pose + o * 16, nb * 16 * sizeof(float),
                                      cudaMemcpyDeviceToHost, m->s_out));
       STA_CHECK_CUDA(cudaMemcpyAsync(pose_conf_out_host + o, d_pconf + o, nb * sizeof(float), cudaMemcpyDeviceToHost,
@@ -1286,6 +1304,20 @@ int sta_op_cast_f32_bf16(const float* in, void* out_bf16, int64_t rows, int C, i
 int sta_op_rope2d(void* tokens_bf16, const int64_t* pos, int B, int N, int H, void* stream) {
   return launch_rope2d(static_cast<bf16*>(tokens_bf16), reinterpret_cast<const long long*>(pos), B, N, H,
                        static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------
+// pointmap consumers (pointmap.cu)
+// ---------------------------------------------------------------------------
+size_t sta_pointmap_scratch_bytes(int V) { return pointmap_scratch_bytes(V); }
+int sta_pointmap_consumers(const float* pts3d, const float* conf, int V, int H, int W, int shared, float* K_out,
+                           float* depth_out, float* conf_mean_out, void* scratch, void* stream) {
+  return launch_pointmap_consumers(pts3d, conf, V, H, W, shared, K_out, depth_out, conf_mean_out, scratch,
+                                   static_cast<cudaStream_t>(stream));
+}
+int sta_depth_scale(const float* Di, const float* Dj, const float* ci, const float* cj, int64_t n, float* out2,
+                    void* scratch, void* stream) {
+  return launch_depth_scale(Di, Dj, ci, cj, static_cast<long long>(n), out2, scratch, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
