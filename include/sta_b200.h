@@ -156,13 +156,26 @@ int sta_op_cast_f32_bf16(const float* in, void* out_bf16, int64_t rows, int C, i
 int sta_op_rope2d(void* tokens_bf16, const int64_t* pos, int B, int N, int H, void* stream);
 
 
+/* ---- keyframe step: OnlineSLAM.regress_two_views (vista_slam/slam.py:153-189) for K edges
+ * (i, j_k) at once, from cached encoder features: symmetric decoder on the K feature pairs, head_pose_s on both
+ * pose tokens, head_pts on both views, then estimate_intrinsic_from_pts3d(shared_intrinsic=True) per edge,
+ * depths = pts3d[..., 2] and conf.mean().  Token positions are the regular (y, x) grid of PositionGetter
+ * (sta_blocks.py:235-247), which is what slam.py:145 caches.  All outputs are [2][K]...: block 0 = the (i -> j)
+ * direction ("ij"), block 1 = "ji".  intri_out [K][3][3], depth_out, conf_mean_out [2][K] may be NULL; scratch as for
+ * sta_pointmap_consumers with V = 2K (only needed when intri_out / depth_out / conf_mean_out is given).
+ * No host synchronisation: the caller decides when to read rel_pose_conf (slam.py:169). ---- */
+int sta_regress_pairs(StaModel* m, const float* feat_i_dev, const float* feat_j_dev, int K, int H, int W,
+                      float* pose_out_dev, float* pose_conf_out_dev, float* pts3d_out_dev, float* conf_out_dev,
+                      float* intri_out_dev, float* depth_out_dev, float* conf_mean_out_dev, void* scratch, void* stream);
+
 /* ---- pointmap consumers: what OnlineSLAM.regress_two_views / connect_view_i_j compute from
  * the head outputs right after the boundary.  Device pointers, fp32; `scratch` is a caller-owned device buffer of
  * sta_pointmap_scratch_bytes(V) bytes (8-byte aligned).  No host synchronisation. ---- */
 size_t sta_pointmap_scratch_bytes(int V);
 /* estimate_intrinsic_from_pts3d (vista_slam/utils/slam_utils.py:8-79, call site slam.py:184) fused with
  * depths = pts3d[..., 2] (slam.py:185) and conf.mean() per view (pose_graph.py:41).
- * pts3d [V][H][W][3], conf [V][H][W]; shared != 0 -> K_out [3][3], else [V][3][3];
+ * pts3d [V][H][W][3], conf [V][H][W]; shared = 0 -> K_out [V][3][3]; 1 -> one K_out [3][3] over all views;
+ * 2 -> K_out [V/2][3][3], edge e from its two views (e, e + V/2), i.e. shared_intrinsic=True per (ij, ji) pair;
  * depth_out [V][H][W] and conf_mean_out [V] may be NULL. */
 int sta_pointmap_consumers(const float* pts3d, const float* conf, int V, int H, int W, int shared, float* K_out,
                            float* depth_out, float* conf_mean_out, void* scratch, void* stream);

@@ -1,0 +1,74 @@
+"""GPU: the batched keyframe step (vista_slam_b200/keyframe.py -> sta_regress_pairs) against
+the per-edge call sequence of OnlineSLAM.regress_two_views (slam.py:153-189) issued through the reference-shaped
+module methods, against the fused pair path (hence, transitively, the oracle / golden vectors of test_model_gpu.py),
+and against the numpy oracle of the pointmap consumers."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import slam_utils_oracle as orc
+from oracle.sta_oracle import make_images
+
+pytestmark = pytest.mark.gpu
+
+
+def maxn(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def test_batched_edges_match_per_edge_reference_sequence(cuda_model):
+    from vista_slam_b200.keyframe import KeyframeFrontend
+    from vista_slam_b200.utils import slam_utils as su
+    H, W = 64, 80
+    imgs, _ = make_images(4, H, W, 99)
+    ts = torch.tensor([[H, W]])
+    kf = KeyframeFrontend(cuda_model)
+    for b in range(4):
+        assert kf.add_view(imgs[b:b + 1].cuda(), ts) == b
+    i, js = 3, [2, 1, 0]
+    res = kf.regress_views(i, js)
+    assert res["pose"].shape == (3, 4, 4) and res["pts3d"].shape == (2, 3, H, W, 3) and res["intri"].shape == (3, 3, 3)
+    grid = torch.cartesian_prod(torch.arange(H // 16), torch.arange(W // 16)).view(1, -1, 2).cuda()
+    for e, j in enumerate(js):
+        fi, fj = kf.enc_features[i], kf.enc_features[j]
+        d_ij, d_ji = cuda_model._decode_stereo(fi, fj, grid, grid)
+        pose = cuda_model.head_pose_s(d_ij[-1][:, 0, :])
+        r_ij = cuda_model.head_pts([fi] + [t[:, 1:, :] for t in d_ij], ts)
+        r_ji = cuda_model.head_pts([fj] + [t[:, 1:, :] for t in d_ji], ts)
+        # same kernels on the same operands; batching only changes tile scheduling -> tight bounds
+        assert maxn(res["pose"][e:e + 1], pose["pose"]) < 5e-3
+        assert maxn(res["pose_conf"][e:e + 1], pose["conf"]) < 2e-3
+        assert maxn(res["pts3d"][0, e:e + 1], r_ij["pts3d"]) < 2e-2
+        assert maxn(res["pts3d"][1, e:e + 1], r_ji["pts3d"]) < 2e-2
+        assert maxn(res["conf"][0, e:e + 1], r_ij["conf"]) < 2e-2
+        # pointmap consumers of THIS step's outputs: numpy oracle on the same pointmaps
+        pcls = torch.cat([res["pts3d"][0, e:e + 1], res["pts3d"][1, e:e + 1]], dim=0)
+        confs = torch.cat([res["conf"][0, e:e + 1], res["conf"][1, e:e + 1]], dim=0)
+        K_ref = orc.estimate_intrinsic_from_pts3d(pcls.cpu().numpy(), confs.cpu().numpy(), True)
+        assert np.allclose(res["intri"][e].cpu().numpy(), K_ref, rtol=1e-4, atol=1e-4)
+        assert torch.equal(res["depths"][:, e], pcls[..., 2])
+        assert np.allclose(res["conf_mean"][:, e].cpu().numpy(), confs.reshape(2, -1).double().mean(1).cpu().numpy(),
+                           rtol=1e-5)
+        assert np.allclose(su.estimate_intrinsic_from_pts3d(pcls, confs, True).cpu().numpy(), K_ref, rtol=1e-4, atol=1e-4)
+    # K = 1 convenience form keeps the reference's return convention
+    pose, pconf, confs, intri, depths = kf.regress_two_views(3, 2)
+    assert pose.shape == (1, 4, 4) and confs.shape == (2, H, W) and intri.shape == (3, 3) and depths.shape == (2, H, W)
+    assert maxn(pose, res["pose"][0:1]) < 5e-3
+
+
+def test_keyframe_step_equals_fused_pair_path(cuda_model):
+    from vista_slam_b200.keyframe import KeyframeFrontend
+    H, W = 48, 64
+    img1, img2 = make_images(2, H, W, 5)
+    main, sup = cuda_model.forward_pairs(img1.cuda(), img2.cuda())
+    ts = torch.tensor([[H, W]])
+    for b in range(2):
+        kf = KeyframeFrontend(cuda_model)
+        kf.add_view(img1[b:b + 1].cuda(), ts)
+        kf.add_view(img2[b:b + 1].cuda(), ts)
+        r = kf.regress_views(0, [1])
+        assert maxn(r["pts3d"][0], main["pts3d_pred"][b:b + 1]) < 2e-2
+        assert maxn(r["pts3d"][1], sup["pts3d_pred"][b:b + 1]) < 2e-2
+        assert maxn(r["pose"], main["relative_pose"][b:b + 1]) < 5e-3
+        assert maxn(r["pose_ji"], sup["relative_pose"][b:b + 1]) < 5e-3

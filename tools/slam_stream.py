@@ -1,0 +1,83 @@
+"""Latency of the SLAM-mode call sequence on synthetic keyframes:
+per keyframe ONE _encode_image (B=1) and, per edge to an earlier keyframe, _decode_stereo + head_pose_s +
+2 x head_pts + estimate_intrinsic_from_pts3d -- first exactly as OnlineSLAM.regress_two_views (slam.py:153-189) issues
+them through the reference-shaped module methods, then through the batched keyframe step."""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", default="224x224")
+    ap.add_argument("--keyframes", type=int, default=12)
+    ap.add_argument("--edges", type=int, default=2)
+    a = ap.parse_args()
+    H, W = [int(v) for v in a.size.split("x")]
+    from oracle.sta_oracle import make_state_dict
+    from vista_slam_b200.sta_model.sta_model import SymmetricTwoViewAssociation as STA
+    from vista_slam_b200.utils import slam_utils as su
+    dev = torch.device("cuda")
+    m = STA()
+    m.load_state_dict(make_state_dict(0), strict=True)
+    m = m.to(dev).eval()
+    g = torch.Generator().manual_seed(1)
+    imgs = [(torch.rand(1, 3, H, W, generator=g) * 2 - 1).to(dev) for _ in range(a.keyframes)]
+    shape = torch.tensor([[H, W]])
+
+    def sync():
+        torch.cuda.synchronize()
+
+    # ---- reference-shaped sequence ----
+    feats, poss = [], []
+    t_enc, t_edge = [], []
+    for i, im in enumerate(imgs):
+        sync(); t0 = time.perf_counter()
+        f, p = m._encode_image(im, shape, normalize=False)
+        sync(); t_enc.append(time.perf_counter() - t0)
+        feats.append(f); poss.append(p)
+        for j in range(max(0, i - a.edges), i):
+            sync(); t0 = time.perf_counter()
+            d_ij, d_ji = m._decode_stereo(feats[i], feats[j], poss[i], poss[j])
+            pose = m.head_pose_s(d_ij[-1][:, 0, :])
+            conf_ij = float(pose["conf"])          # the host sync of slam.py:169
+            r_ji = m.head_pts([feats[j]] + [t[:, 1:, :].float() for t in d_ji], shape)
+            r_ij = m.head_pts([feats[i]] + [t[:, 1:, :].float() for t in d_ij], shape)
+            pcls = torch.cat([r_ij["pts3d"], r_ji["pts3d"]], dim=0)
+            confs = torch.cat([r_ij["conf"], r_ji["conf"]], dim=0)
+            intri = su.estimate_intrinsic_from_pts3d(pcls, confs, shared_intrinsic=True)
+            depths = pcls[..., 2]
+            sync(); t_edge.append(time.perf_counter() - t0)
+    skip = 2
+    enc_ms = 1e3 * sum(t_enc[skip:]) / len(t_enc[skip:])
+    edge_ms = 1e3 * sum(t_edge[skip:]) / max(1, len(t_edge[skip:]))
+    print("reference-shaped calls %dx%d: encode %.3f ms/keyframe, edge %.3f ms (%d edges/keyframe) -> %.3f ms/keyframe" %
+          (H, W, enc_ms, edge_ms, a.edges, enc_ms + a.edges * edge_ms), flush=True)
+
+    # ---- batched keyframe step ----
+    try:
+        from vista_slam_b200.keyframe import KeyframeFrontend
+    except ImportError:
+        return
+    kf = KeyframeFrontend(m)
+    t_step = []
+    for i, im in enumerate(imgs):
+        sync(); t0 = time.perf_counter()
+        idx = kf.add_view(im, shape)
+        js = list(range(max(0, i - a.edges), i))
+        if js:
+            res = kf.regress_views(idx, js)
+            _ = res["pose_conf"].cpu()              # ONE host sync per keyframe
+        sync(); t_step.append(time.perf_counter() - t0)
+    step_ms = 1e3 * sum(t_step[skip + 1:]) / len(t_step[skip + 1:])
+    print("batched keyframe step %dx%d: %.3f ms/keyframe (encode + %d edges in one decode batch)" % (H, W, step_ms, a.edges),
+          flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -60,6 +60,7 @@ def lib():
     L.sta_decode.argtypes = [vp, vp, vp, vp, vp, i, i, POINTER(vp), POINTER(vp), vp]
     L.sta_head_pose.argtypes = [vp, vp, i, vp, vp, vp]
     L.sta_head_pts.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp, vp, vp]
+    L.sta_regress_pairs.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.sta_forward_pairs.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
     L.sta_forward_pairs_host.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
     L.sta_launch_count.argtypes = [vp]

@@ -74,7 +74,8 @@ pointmap_stats_kernel(const float* __restrict__ pts3d, const float* __restrict__
   block_reduce_store<5>(s, partial + (static_cast<long long>(v) * kStatBlocks + blockIdx.x) * kStatVals);
 }
 
-// one block of 32 threads; shared != 0: one K for all views, else one per view
+// one block of 32 threads; shared == 0: one K per view, 1: one K for all views, 2: one K per edge e < V/2 from
+// its two views (e, e + V/2) -- the [ij ; ji] concatenation of slam.py:181-184 for a batch of edges
 __global__ void pointmap_finalize_kernel(const double* __restrict__ partial, int V, int H, int W, int shared,
                                          float* __restrict__ K_out, float* __restrict__ conf_mean_out) {
   pdl_wait();
@@ -86,6 +87,18 @@ __global__ void pointmap_finalize_kernel(const double* __restrict__ partial, int
     for (int b = 0; b < kStatBlocks; ++b)
       for (int i = 0; i < 5; ++i) t[i] += partial[(static_cast<long long>(v) * kStatBlocks + b) * kStatVals + i];
     if (conf_mean_out) conf_mean_out[v] = static_cast<float>(t[4] / (static_cast<double>(H) * W));
+    if (shared == 2 && v < V / 2) {
+      double u[4];
+      for (int i = 0; i < 4; ++i) {
+        double t2 = 0.0;
+        for (int b = 0; b < kStatBlocks; ++b) t2 += partial[(static_cast<long long>(v + V / 2) * kStatBlocks + b) * kStatVals + i];
+        u[i] = t[i] + t2;
+      }
+      float* K = K_out + v * 9;
+      K[0] = static_cast<float>(u[0] / u[1]); K[1] = 0.f; K[2] = cx;
+      K[3] = 0.f; K[4] = static_cast<float>(u[2] / u[3]); K[5] = cy;
+      K[6] = 0.f; K[7] = 0.f; K[8] = 1.f;
+    }
     if (!shared) {
       float* K = K_out + v * 9;
       K[0] = static_cast<float>(t[0] / t[1]); K[1] = 0.f; K[2] = cx;
@@ -93,7 +106,7 @@ __global__ void pointmap_finalize_kernel(const double* __restrict__ partial, int
       K[6] = 0.f; K[7] = 0.f; K[8] = 1.f;
     }
   }
-  if (shared && threadIdx.x == 0) {
+  if (shared == 1 && threadIdx.x == 0) {
     for (int v = 0; v < V; ++v) {  // fixed order
       for (int i = 0; i < 4; ++i) {
         double t = 0.0;
@@ -145,6 +158,7 @@ int launch_pointmap_consumers(const float* pts3d, const float* conf, int V, int 
                               float* depth_out, float* conf_mean_out, void* scratch, cudaStream_t stream) {
   STA_REQUIRE(pts3d && conf && K_out && scratch, "null pointer");
   STA_REQUIRE(V > 0 && V <= 65535 && H > 0 && W > 0 && static_cast<long long>(H) * W < (1ll << 30), "bad shape");
+  STA_REQUIRE(shared >= 0 && shared <= 2 && (shared != 2 || V % 2 == 0), "shared: 0 per view, 1 all views, 2 per edge (V even)");
   STA_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 7) == 0, "scratch must be 8-byte aligned");
   double* partial = static_cast<double*>(scratch);
   STA_CHECK_CUDA(launch_pdl(pointmap_stats_kernel, dim3(kStatBlocks, V), dim3(256), 0, stream, 1, pts3d, conf, H, W,

@@ -1113,6 +1113,50 @@ int sta_head_pts(StaModel* m, const float* enc_feat_dev, const float* dec6_dev, 
   return run_dpt(c, ws, B, h, w, k0, k1, k2, k3, pts3d_out_dev, conf_out_dev);
 }
 
+int sta_regress_pairs(StaModel* m, const float* feat_i_dev, const float* feat_j_dev, int K, int H, int W,
+                      float* pose_out_dev, float* pose_conf_out_dev, float* pts3d_out_dev, float* conf_out_dev,
+                      float* intri_out_dev, float* depth_out_dev, float* conf_mean_out_dev, void* scratch, void* stream) {
+  RUN(check_ready(m));
+  STA_REQUIRE(K > 0 && K <= m->max_pairs_per_chunk, "edge batch must be in [1, 16]");
+  STA_REQUIRE(H % 16 == 0 && W % 16 == 0 && H > 0 && W > 0, "image size must be a positive multiple of 16");
+  STA_REQUIRE(H / 16 <= 1024 && W / 16 <= 1024, "token grid exceeds the RoPE table");
+  STA_REQUIRE(feat_i_dev && feat_j_dev && pose_out_dev && pose_conf_out_dev && pts3d_out_dev && conf_out_dev,
+              "null pointer");
+  Ctx c{m, static_cast<cudaStream_t>(stream)};
+  const int h = H / 16, w = W / 16, N = h * w, S = 2 * K, M = N + 1;
+  RUN(ensure_ws(m, S, h, w));
+  Workspace& ws = m->ws;
+  DecBufs d = take_dec(ws, S, N);
+  m->launches += 3;
+  RUN(launch_cast_f32_bf16(feat_i_dev, d.enc_bf16, static_cast<long long>(K) * N, kEncDim, 0, c.st));
+  RUN(launch_cast_f32_bf16(feat_j_dev, d.enc_bf16 + static_cast<size_t>(K) * N * kEncDim, static_cast<long long>(K) * N,
+                           kEncDim, 0, c.st));
+  RUN(launch_make_positions(d.pos, S, h, w, 1, c.st));
+  RUN(run_decoder(c, K, N, d, nullptr, nullptr));
+  m->launches += 2;
+  RUN(launch_pose_head(d.xd, static_cast<long long>(M) * kDecDim, K, 1, kLnEps, m->pose, pose_out_dev, pose_conf_out_dev,
+                       c.st));
+  RUN(launch_pose_head(d.xd + static_cast<long long>(K) * M * kDecDim, static_cast<long long>(M) * kDecDim, K, 1, kLnEps,
+                       m->pose, pose_out_dev + static_cast<long long>(K) * 16, pose_conf_out_dev + K, c.st));
+  const long long px = static_cast<long long>(H) * W;
+  for (int v = 0; v < 2; ++v) {
+    const size_t save = ws.off;
+    const size_t tok0 = static_cast<size_t>(v) * K * N;
+    RUN(run_dpt(c, ws, K, h, w, d.enc_bf16 + tok0 * 1024, d.hook[0] + tok0 * 768, d.hook[1] + tok0 * 768,
+                d.hook[2] + tok0 * 768, pts3d_out_dev + static_cast<long long>(v) * K * px * 3,
+                conf_out_dev + static_cast<long long>(v) * K * px));
+    ws.off = save;
+  }
+  if (intri_out_dev || depth_out_dev || conf_mean_out_dev) {
+    STA_REQUIRE(scratch != nullptr && intri_out_dev != nullptr,
+                "the pointmap consumers need the scratch buffer and intri_out (depth_out / conf_mean_out are optional)");
+    m->launches += 2;
+    RUN(launch_pointmap_consumers(pts3d_out_dev, conf_out_dev, S, H, W, 2, intri_out_dev, depth_out_dev,
+                                  conf_mean_out_dev, scratch, c.st));
+  }
+  return 0;
+}
+
 int sta_forward_pairs(StaModel* m, const void* img1_dev, const void* img2_dev, int img_is_bf16, int B, int H, int W,
                       float* pts3d_out_dev, float* conf_out_dev, float* pose_out_dev, float* pose_conf_out_dev,
                       void* stream) {
