@@ -133,6 +133,8 @@ typedef struct StaGemmDesc {
   const float* head_b;  /* EPI_HEAD: [4] */
   float* pts3d;         /* EPI_HEAD: [pixels][3] */
   float* conf;          /* EPI_HEAD: [pixels] */
+  void* splitk_ws;      /* optional fp32 scratch (16-byte aligned): lets small EPI_F32 problems split K across CTAs */
+  int64_t splitk_ws_bytes;
 } StaGemmDesc;
 
 int sta_op_gemm(const StaGemmDesc* d, void* stream);
@@ -167,6 +169,11 @@ int sta_op_rope2d(void* tokens_bf16, const int64_t* pos, int B, int N, int H, vo
 int sta_regress_pairs(StaModel* m, const float* feat_i_dev, const float* feat_j_dev, int K, int H, int W,
                       float* pose_out_dev, float* pose_conf_out_dev, float* pts3d_out_dev, float* conf_out_dev,
                       float* intri_out_dev, float* depth_out_dev, float* conf_mean_out_dev, void* scratch, void* stream);
+
+/* Launch-bound sizes (<= 8192 tokens per call: one keyframe, a few edges) of sta_encode and sta_regress_pairs are
+ * captured into CUDA graphs per (entry point, batch, H, W) on their second use and replayed afterwards
+ * (STA_CUDA_GRAPHS=0 disables).  Number of graph replays so far (tests / diagnostics): */
+int64_t sta_graph_replays(StaModel* m);
 
 /* ---- pointmap consumers: what OnlineSLAM.regress_two_views / connect_view_i_j compute from
  * the head outputs right after the boundary.  Device pointers, fp32; `scratch` is a caller-owned device buffer of

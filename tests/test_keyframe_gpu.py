@@ -51,6 +51,14 @@ def test_batched_edges_match_per_edge_reference_sequence(cuda_model):
         assert np.allclose(res["conf_mean"][:, e].cpu().numpy(), confs.reshape(2, -1).double().mean(1).cpu().numpy(),
                            rtol=1e-5)
         assert np.allclose(su.estimate_intrinsic_from_pts3d(pcls, confs, True).cpu().numpy(), K_ref, rtol=1e-4, atol=1e-4)
+    # the keyframe path really is graph-replayed (4 encodes of one shape: eager, capture + replay, replay, replay)
+    from vista_slam_b200 import _lib
+    assert _lib.lib().sta_graph_replays(cuda_model._handle) >= 3
+    r2 = kf.regress_views(i, js)   # second use of this (K, H, W): captured and replayed
+    r3 = kf.regress_views(i, js)   # replayed
+    for k in ("pose", "pts3d", "conf", "intri", "depths"):
+        assert torch.equal(r2[k], r3[k]), k            # replays are deterministic
+        assert maxn(r2[k], res[k]) < 1e-6, k           # and equal the eager first run
     # K = 1 convenience form keeps the reference's return convention
     pose, pconf, confs, intri, depths = kf.regress_two_views(3, 2)
     assert pose.shape == (1, 4, 4) and confs.shape == (2, H, W) and intri.shape == (3, 3) and depths.shape == (2, H, W)

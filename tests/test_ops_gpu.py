@@ -34,7 +34,7 @@ def test_gemm_shapes_and_tails(capsys):
 
 def test_gemm_fused_epilogues(capsys):
     # gelu, residual x2 + relu copy, relu, BN=128 path, fp32 (in-place reduce-add, plain, separate residual), row map, RoPE, ConvT
-    assert len(_collect(bu.group_gemm_epi, capsys)) == 11
+    assert len(_collect(bu.group_gemm_epi, capsys)) == 19
 
 
 def test_implicit_gemm_conv_and_head(capsys):

@@ -142,6 +142,51 @@ def group_gemm_epi():
     ref = qkv.clone()
     ref[:, :2 * C] = rope_ref(qkv[:, :2 * C].reshape(M, 8, 64), pos).reshape(M, 2 * C)
     report("epi rope", out, ref, 1e-2)
+    # small-problem route (SLAM mode: one 224x224 keyframe = 196 tokens): 128-wide single-CTA tiles, split-K for the
+    # in-place fp32 layers (with scratch), TMA reduce-add without scratch
+    Ms, Ks = 196, 1024
+    As = torch.randn(Ms, Ks, device=dev).bfloat16()
+    Wl = (torch.randn(1024, Ks, device=dev) / math.sqrt(Ks)).bfloat16()
+    bl = torch.randn(1024, device=dev)
+    refs = As.float() @ Wl.float().t() + bl
+    ws = torch.zeros(8 * 256 * 1024, device=dev)
+    for name, kw in (("split-K", dict(splitk_ws=ws, splitk_ws_bytes=ws.numel() * 4)), ("reduce-add", {})):
+        xs = torch.randn(Ms, 1024, device=dev)
+        x0s = xs.clone()
+        run_gemm(gemm_desc(epi=EPI_F32, A=As, lda=Ks, W=Wl, ldw=Ks, M=Ms, N=1024, K=Ks, bias=bl, out=xs, ldo=1024, resid=xs,
+                           **kw))
+        report("small M196 f32 in place (%s)" % name, xs, x0s + refs, 2e-3)
+    ys = torch.zeros(Ms, 1024, device=dev)
+    run_gemm(gemm_desc(epi=EPI_F32, A=As, lda=Ks, W=Wl, ldw=Ks, M=Ms, N=1024, K=Ks, bias=bl, out=ys, ldo=1024,
+                       splitk_ws=ws, splitk_ws_bytes=ws.numel() * 4))
+    report("small M196 f32 no resid (split-K)", ys, refs, 2e-3)
+    outs = torch.zeros(Ms, 1024, device=dev, dtype=torch.bfloat16)
+    run_gemm(gemm_desc(epi=EPI_GELU, A=As, lda=Ks, W=Wl, ldw=Ks, M=Ms, N=1024, K=Ks, bias=bl, out=outs, ldo=1024))
+    report("small M196 gelu", outs, F.gelu(refs), 1e-2)
+    poss = torch.randint(-1, 14, (Ms, 2), device=dev, dtype=torch.int32)
+    run_gemm(gemm_desc(epi=EPI_ROPE, A=As, lda=Ks, W=Wl, ldw=Ks, M=Ms, N=1024, K=Ks, bias=bl, out=outs, ldo=1024, pos=poss,
+                       rope_cols=768))
+    refr = refs.clone()
+    refr[:, :768] = rope_ref(refs[:, :768].reshape(Ms, 12, 64), poss).reshape(Ms, 768)
+    report("small M196 rope", outs, refr, 1e-2)
+    # the same epilogues on a problem wide enough for the 256-wide CTA-pair tiles (TMA-store epilogue, BN = 256)
+    Mw, Kw = 5000, 256
+    Aw = torch.randn(Mw, Kw, device=dev).bfloat16()
+    Ww = (torch.randn(1024, Kw, device=dev) / math.sqrt(Kw)).bfloat16()
+    refw = Aw.float() @ Ww.float().t() + bl
+    outw = torch.zeros(Mw, 1024, device=dev, dtype=torch.bfloat16)
+    run_gemm(gemm_desc(epi=EPI_GELU, A=Aw, lda=Kw, W=Ww, ldw=Kw, M=Mw, N=1024, K=Kw, bias=bl, out=outw, ldo=1024))
+    report("wide M5000 gelu", outw, F.gelu(refw), 1e-2)
+    posw = torch.randint(-1, 70, (Mw, 2), device=dev, dtype=torch.int32)
+    run_gemm(gemm_desc(epi=EPI_ROPE, A=Aw, lda=Kw, W=Ww, ldw=Kw, M=Mw, N=1024, K=Kw, bias=bl, out=outw, ldo=1024, pos=posw,
+                       rope_cols=768))
+    refr = refw.clone()
+    refr[:, :768] = rope_ref(refw[:, :768].reshape(Mw, 12, 64), posw).reshape(Mw, 768)
+    report("wide M5000 rope (positions beyond the smem table)", outw, refr, 1e-2)
+    xw = torch.randn(Mw, 1024, device=dev)
+    xw0 = xw.clone()
+    run_gemm(gemm_desc(epi=EPI_F32, A=Aw, lda=Kw, W=Ww, ldw=Kw, M=Mw, N=1024, K=Kw, bias=bl, out=xw, ldo=1024, resid=xw))
+    report("wide M5000 f32 in place (reduce-add)", xw, xw0 + refw, 2e-3)
     # PIXSHUF: tokens (2 img, 5x7 grid), Cin 128, cout 64, k 2
     nimg, h, w, cin, cout, k = 2, 5, 7, 128, 64, 2
     At = torch.randn(nimg * h * w, cin, device=dev).bfloat16()

@@ -28,6 +28,7 @@ class StaGemmDesc(Structure):
         ("pos", c_void_p), ("rope_cols", c_int),
         ("ps_k", c_int), ("ps_cout", c_int), ("ps_h", c_int), ("ps_w", c_int),
         ("head_w", c_void_p), ("head_b", c_void_p), ("pts3d", c_void_p), ("conf", c_void_p),
+        ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_int64),
     ]
 
 
@@ -60,6 +61,8 @@ def lib():
     L.sta_decode.argtypes = [vp, vp, vp, vp, vp, i, i, POINTER(vp), POINTER(vp), vp]
     L.sta_head_pose.argtypes = [vp, vp, i, vp, vp, vp]
     L.sta_head_pts.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp, vp, vp]
+    L.sta_graph_replays.argtypes = [vp]
+    L.sta_graph_replays.restype = i64
     L.sta_regress_pairs.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.sta_forward_pairs.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
     L.sta_forward_pairs_host.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp]

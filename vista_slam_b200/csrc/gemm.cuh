@@ -55,6 +55,10 @@ struct GemmParams {
   const float* head_b;  // [4]
   float* pts3d;         // [pixels][3]
   float* conf;          // [pixels]
+  // split-K (TMA epilogue, EPI_F32 only): a work item is (m, n, ks); split ks accumulates k-blocks
+  // [ks * nkb / ksplit, (ks + 1) * nkb / ksplit) and stores its fp32 partial tile at output row ks * split_rows + row
+  int ksplit;      // >= 1
+  int split_rows;  // rows of one partial slice (multiple of 128)
   int c_reduce;         // TMA epilogue, EPI_F32: out += result (in-place fp32 residual stream) via bulk reduce-add
   long long* dbg;       // optional clock64 trace (env STA_GEMM_TRACE), else null
 };
@@ -424,7 +428,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
 // ---------------------------------------------------------------------------
 template <int BN, int EPI, int EW, typename Release>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmC, uint32_t taddr, int m_tile,
-                                                  int n_tile, int quarter, int part, uint8_t* cbuf, const float* rope_s,
+                                                  int n_tile, int row_off, int quarter, int part, uint8_t* cbuf,
+                                                  const float* rope_s,
                                                   uint64_t* tfull_bar, uint32_t tfull_phase, Release&& release,
                                                   long long* trace) {
   constexpr int PARTS = EW / 4;
@@ -436,7 +441,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   constexpr bool OUT_F32 = (EPI == EPI_F32);
   const int lane = threadIdx.x & 31;
   const int colbase = n_tile * BN + part * CH;
-  const int row0 = m_tile * 128 + quarter * 32;
+  const int row0 = m_tile * 128 + quarter * 32;  // first row of this warp's box (token index)
+  const int srow0 = row0 + row_off;              // ... in the output tensor (split-K partial slices)
   const uint32_t cb = smem_u32(cbuf);
   const uint32_t srow = cb + lane * 128;  // this thread's row inside the box
   const uint32_t sx = lane & 7;           // 128B swizzle: 16-byte chunk j lives at j ^ (row & 7)
@@ -527,8 +533,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        if (p.c_reduce) tma_reduce_add_2d(tmC, cbuf, col, row0);
-        else tma_store_2d(tmC, cbuf, col, row0);
+        if (p.c_reduce) tma_reduce_add_2d(tmC, cbuf, col, srow0);
+        else tma_store_2d(tmC, cbuf, col, srow0);
         tma_store_commit();
       }
     } else {
@@ -548,7 +554,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(tmC, cbuf, col - 32, row0);
+          tma_store_2d(tmC, cbuf, col - 32, srow0);
           tma_store_commit();
         }
       }
@@ -565,7 +571,7 @@ __global__ void __launch_bounds__(GemmCfg<BN, CG, EW, EPI, TMA>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using Cfg = GemmCfg<BN, CG, EW, EPI, TMA>;
-  static_assert(!TMA || (AMODE == A_LINEAR && BN == 256 &&
+  static_assert(!TMA || (AMODE == A_LINEAR && (BN == 256 || BN == 128) &&
                          (EPI == EPI_BF16 || EPI == EPI_GELU || EPI == EPI_F32 || EPI == EPI_ROPE)),
                 "TMA-store epilogue: wide linear layers only");
   constexpr int STAGES = Cfg::STAGES;
@@ -594,7 +600,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m_tiles128 = (AMODE == A_CONV3) ? p.nimg * p.tiles_h * p.tiles_w : (p.M + 127) / 128;
   const int m_tiles = (m_tiles128 + CG - 1) / CG;
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
+  const int ksplit = TMA ? p.ksplit : 1;
+  const int num_tiles = m_tiles * n_tiles * ksplit;  // work items (m, n, ks), ks fastest
   const int cpb = (AMODE == A_CONV3) ? (p.Cin / 64) : 1;  // 64-channel chunks per filter tap
   const int nkb = (AMODE == A_CONV3) ? 9 * cpb : (p.K + 63) / 64;
   const int first_tile = blockIdx.x / CG;
@@ -649,8 +656,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-        const int m_tile = (tile / n_tiles) * CG + static_cast<int>(cta_rank);  // this CTA's 128-row tile
-        const int n_tile = tile % n_tiles;
+        const int ks = tile % ksplit, mn = tile / ksplit;
+        const int m_tile = (mn / n_tiles) * CG + static_cast<int>(cta_rank);  // this CTA's 128-row tile
+        const int n_tile = mn % n_tiles;
+        const int kb0 = ks * nkb / ksplit, kb1 = (ks + 1) * nkb / ksplit;
         const int b_row0 = n_tile * BN + static_cast<int>(cta_rank) * (BN / CG);
         int cn = 0, ch0 = 0, cw0 = 0;
         if constexpr (AMODE == A_CONV3) {
@@ -661,7 +670,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ch0 = th * 8;
           cw0 = (t - th * p.tiles_w) * 16;
         }
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (CG == 1 || leader) mbar_arrive_expect_tx(&full[stage], CG * (A_BYTES + B_BYTES));
           if constexpr (AMODE == A_CONV3) {
@@ -703,7 +712,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (trc) p.dbg[256 + 4 * tcount + 1] = clock64();
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int ks = tile % ksplit;
+        const int kb0 = ks * nkb / ksplit, kb1 = (ks + 1) * nkb / ksplit;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * A_BYTES));
@@ -712,9 +723,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < 4; ++k) {
             // advance 16 K-elements = 32 bytes inside the 128B swizzle atom (encoded >> 4)
             if constexpr (CG == 2)
-              umma_bf16_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
             else
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
           }
           if constexpr (CG == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -732,8 +743,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-      const int m_tile = (tile / n_tiles) * CG + static_cast<int>(cta_rank);
-      const int n_tile = tile % n_tiles;
+      const int ks = tile % ksplit, mn = tile / ksplit;
+      const int m_tile = (mn / n_tiles) * CG + static_cast<int>(cta_rank);
+      const int n_tile = mn % n_tiles;
       const int tcount = (tile - first_tile) / tile_step;
       const bool trc = p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && tcount < 40;
       if (trc) p.dbg[4 * tcount + 0] = clock64();
@@ -748,7 +760,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
       if constexpr (TMA) {
-        epilogue_tile_tma<BN, EPI, EW>(p, &tmC, taddr, m_tile, n_tile, quarter, part,
+        epilogue_tile_tma<BN, EPI, EW>(p, &tmC, taddr, m_tile, n_tile, ks * p.split_rows, quarter, part,
                                        stg_all + (warp - 4) * Cfg::STG_WARP_BYTES, rope_s, &tfull[acc], acc_phase, release,
                                        (trc && tcount < 16) ? p.dbg + 512 + 16 * tcount : nullptr);
       } else {

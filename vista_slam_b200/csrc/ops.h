@@ -22,6 +22,9 @@ struct GemmLaunch {
   const bf16* Wt = nullptr;
   long long ldw = 0;
   GemmParams p = {};
+  // optional fp32 scratch for split-K partials (small, weight-streaming-bound problems); unused if null
+  void* splitk_ws = nullptr;
+  size_t splitk_ws_bytes = 0;
 };
 
 int launch_gemm(const GemmLaunch& g, cudaStream_t stream);

@@ -189,6 +189,20 @@ struct StaModel {
   int64_t launches = 0;
   int max_pairs_per_chunk = 16;
 
+  // ---- CUDA-graph replay of the launch-bound small-batch entry points (SLAM mode) ----
+  struct GraphEntry {
+    std::vector<long long> key;
+    cudaGraphExec_t exec = nullptr;  // null: seen once (ran eagerly), capture on the next call
+    int64_t launches = 0;
+    bool unsupported = false;  // capture / instantiate failed once: stay eager for this key
+  };
+  float* splitk_ws = nullptr;  // fp32 partial tiles of the split-K route for small problems (gemm.cu)
+  static constexpr size_t kSplitKBytes = static_cast<size_t>(48) << 20;
+  std::vector<GraphEntry> graphs;
+  cudaStream_t s_cap = nullptr;  // capture stream (the caller's stream may be the legacy default stream)
+  int graph_mode = -1;           // env STA_CUDA_GRAPHS (default on)
+  int64_t graph_replays = 0;
+
   // ---- optional per-kernel-family timing (CUDA events on the launch stream) ----
   bool prof_on = false;
   struct ProfRec { int cat; cudaEvent_t e0, e1; };
@@ -418,6 +432,8 @@ int gemm(const Ctx& c, int amode, int epi, const bf16* A, long long lda, const L
   g.epi = epi;
   g.A = A;
   g.lda = lda;
+  g.splitk_ws = c.m->splitk_ws;
+  g.splitk_ws_bytes = c.m->splitk_ws ? StaModel::kSplitKBytes : 0;
   g.Wt = L.w;
   g.ldw = L.K;
   p.N = L.N;
@@ -534,13 +550,18 @@ size_t ws_need(int nimg, int h, int w) {
   for (int i = 0; i < 5; ++i) add(nimg * P1 * 256 * 2);       // t1, t2, s_raw, s_relu, o
   add(nimg * 64 * N * 256 * 2); add(nimg * 64 * N * 256 * 2);  // up, path (up to 8h x 8w)
   add(nimg * 64 * N * 128 * 2); add(nimg * 256 * N * 128 * 2); // hc1, hup (full res)
+  // static outputs of the graph-replayed keyframe step: pts3d, conf, depth (fp32, full res), poses, K, reduction scratch
+  add(nimg * 256 * N * 5 * 4); add(nimg * 32 * 4); add(pointmap_scratch_bytes(nimg));
   return b + (1 << 20);
 }
+
+void drop_graphs(StaModel* m);
 
 int ensure_ws(StaModel* m, int nimg, int h, int w) {
   const size_t need = ws_need(nimg, h, w);
   if (m->ws.bytes < need) {
     STA_CHECK_CUDA(cudaDeviceSynchronize());
+    drop_graphs(m);  // they point into the old workspace
     if (m->ws.base) STA_CHECK_CUDA(cudaFree(m->ws.base));
     m->ws.base = nullptr;
     m->ws.bytes = 0;
@@ -551,6 +572,75 @@ int ensure_ws(StaModel* m, int nimg, int h, int w) {
   m->ws.nimg = nimg;
   m->ws.h = h;
   m->ws.w = w;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Small-batch calls (one keyframe, a handful of edges) are launch-bound: ~170-400 kernels of a few microseconds each.
+// run_graphed() runs `body(ctx)` eagerly the first time a key is seen (lazy initialisation such as
+// cudaFuncSetAttribute / the RoPE table happens there), captures it into a CUDA graph on the second call (on a private
+// stream -- the caller's may be the legacy default stream -- with the programmatic-dependent-launch edges kept) and
+// replays the instantiated graph on the caller's stream from then on.  `body` must only touch memory whose
+// addresses are a function of the key (workspace offsets for that shape, weights): user pointers are handled by
+// the caller outside the graph.  Graphs die with the workspace they point into.
+// ---------------------------------------------------------------------------
+constexpr long long kGraphMaxTokens = 8192;  // only launch-bound problem sizes
+
+void drop_graphs(StaModel* m) {
+  for (auto& g : m->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  m->graphs.clear();
+}
+
+bool graphs_enabled(StaModel* m) {
+  if (m->graph_mode < 0) {
+    const char* e = getenv("STA_CUDA_GRAPHS");
+    m->graph_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return m->graph_mode == 1 && !m->prof_on;
+}
+
+template <typename Body>
+int run_graphed(StaModel* m, cudaStream_t st, const std::vector<long long>& key, Body&& body) {
+  if (!graphs_enabled(m)) return body(Ctx{m, st});
+  StaModel::GraphEntry* ent = nullptr;
+  for (auto& g : m->graphs)
+    if (g.key == key) ent = &g;
+  if (!ent) {
+    if (m->graphs.size() >= 32) drop_graphs(m);
+    m->graphs.emplace_back();
+    m->graphs.back().key = key;
+    return body(Ctx{m, st});  // first sighting: eager
+  }
+  if (ent->unsupported) return body(Ctx{m, st});
+  if (!ent->exec) {
+    if (!m->s_cap) STA_CHECK_CUDA(cudaStreamCreateWithFlags(&m->s_cap, cudaStreamNonBlocking));
+    const int64_t l0 = m->launches;
+    STA_CHECK_CUDA(cudaStreamBeginCapture(m->s_cap, cudaStreamCaptureModeThreadLocal));
+    const int rc = body(Ctx{m, m->s_cap});
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(m->s_cap, &graph);
+    if (rc != 0) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return rc;
+    }
+    cudaGraphExec_t exec = nullptr;
+    if (ce != cudaSuccess || graph == nullptr || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();  // clear; fall back to eager launches for this key
+      ent->unsupported = true;
+      m->launches = l0;
+      return body(Ctx{m, st});
+    }
+    cudaGraphDestroy(graph);
+    ent->exec = exec;
+    ent->launches = m->launches - l0;
+    m->launches = l0;
+  }
+  STA_CHECK_CUDA(cudaGraphLaunch(ent->exec, st));
+  m->launches += ent->launches;
+  m->graph_replays++;
   return 0;
 }
 
@@ -878,6 +968,10 @@ int sta_create(StaModel** out) {
     return 1;
   }
   cudaMemset(m->arena, 0, m->arena_bytes);
+  if (cudaMalloc(&m->splitk_ws, StaModel::kSplitKBytes) != cudaSuccess) {
+    cudaGetLastError();
+    m->splitk_ws = nullptr;  // the split-K route is simply not taken
+  }
   build_registry(m);
   if (m->arena_off > m->arena_bytes) {
     set_last_error("internal: weight arena too small");
@@ -896,6 +990,9 @@ void sta_destroy(StaModel* m) {
   if (m->ws.base) cudaFree(m->ws.base);
   if (m->stage) cudaFree(m->stage);
   if (m->io) cudaFree(m->io);
+  if (m->splitk_ws) cudaFree(m->splitk_ws);
+  drop_graphs(m);
+  if (m->s_cap) cudaStreamDestroy(m->s_cap);
   if (m->s_in) {
     cudaStreamDestroy(m->s_in);
     cudaStreamDestroy(m->s_out);
@@ -1049,10 +1146,24 @@ int sta_encode(StaModel* m, const void* img_dev, int img_is_bf16, int B, int H, 
   const int h = H / 16, w = W / 16, N = h * w;
   RUN(ensure_ws(m, B, h, w));
   EncBufs e = take_enc(m->ws, B, N);
-  m->launches += 2;
+  m->launches += 1;
   RUN(launch_patch_im2col(img_dev, img_is_bf16, B, H, W, e.patches, c.st));
-  RUN(launch_make_positions(e.pos, B, h, w, 0, c.st));
-  RUN(run_encoder(c, B, N, feat_out_dev, e));
+  // launch-bound sizes: the encoder proper is replayed as a CUDA graph on workspace buffers, the features are
+  // then copied to the caller's tensor (which is long-lived: slam.py:145 keeps it for the whole run)
+  const bool graphed = static_cast<long long>(B) * N <= kGraphMaxTokens;
+  float* x = graphed ? m->ws.take<float>(static_cast<size_t>(B) * N * kEncDim) : feat_out_dev;
+  auto body = [&](const Ctx& cc) -> int {
+    m->launches += 1;
+    RUN(launch_make_positions(e.pos, B, h, w, 0, cc.st));
+    return run_encoder(cc, B, N, x, e);
+  };
+  if (graphed) {
+    RUN(run_graphed(m, c.st, {1, B, H, W}, body));
+    STA_CHECK_CUDA(cudaMemcpyAsync(feat_out_dev, x, static_cast<size_t>(B) * N * kEncDim * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, c.st));
+  } else {
+    RUN(body(c));
+  }
   if (pos_out_dev) {
     const long long n = 2LL * B * N;
     m->launches++;
@@ -1113,6 +1224,8 @@ int sta_head_pts(StaModel* m, const float* enc_feat_dev, const float* dec6_dev, 
   return run_dpt(c, ws, B, h, w, k0, k1, k2, k3, pts3d_out_dev, conf_out_dev);
 }
 
+int64_t sta_graph_replays(StaModel* m) { return m ? m->graph_replays : 0; }
+
 int sta_regress_pairs(StaModel* m, const float* feat_i_dev, const float* feat_j_dev, int K, int H, int W,
                       float* pose_out_dev, float* pose_conf_out_dev, float* pts3d_out_dev, float* conf_out_dev,
                       float* intri_out_dev, float* depth_out_dev, float* conf_mean_out_dev, void* scratch, void* stream) {
@@ -1127,32 +1240,68 @@ int sta_regress_pairs(StaModel* m, const float* feat_i_dev, const float* feat_j_
   RUN(ensure_ws(m, S, h, w));
   Workspace& ws = m->ws;
   DecBufs d = take_dec(ws, S, N);
-  m->launches += 3;
+  const bool consumers = intri_out_dev || depth_out_dev || conf_mean_out_dev;
+  if (consumers)
+    STA_REQUIRE(scratch != nullptr && intri_out_dev != nullptr,
+                "the pointmap consumers need the scratch buffer and intri_out (depth_out / conf_mean_out are optional)");
+  const long long px = static_cast<long long>(H) * W;
+  // Launch-bound sizes: everything after the input casts is replayed as a CUDA graph that writes workspace
+  // buffers; the results are then copied to the caller's tensors.  Large batches write the caller's tensors directly.
+  const bool graphed = static_cast<long long>(S) * M <= kGraphMaxTokens;
+  float *o_pose = pose_out_dev, *o_pconf = pose_conf_out_dev, *o_pts = pts3d_out_dev, *o_conf = conf_out_dev;
+  float *o_intri = intri_out_dev, *o_depth = depth_out_dev, *o_cmean = conf_mean_out_dev;
+  void* o_scratch = scratch;
+  if (graphed) {
+    o_pose = ws.take<float>(static_cast<size_t>(S) * 16);
+    o_pconf = ws.take<float>(S);
+    o_pts = ws.take<float>(static_cast<size_t>(S) * px * 3);
+    o_conf = ws.take<float>(static_cast<size_t>(S) * px);
+    if (consumers) {
+      o_intri = ws.take<float>(static_cast<size_t>(K) * 9);
+      o_depth = depth_out_dev ? ws.take<float>(static_cast<size_t>(S) * px) : nullptr;
+      o_cmean = conf_mean_out_dev ? ws.take<float>(S) : nullptr;
+      o_scratch = ws.take<double>(pointmap_scratch_bytes(S) / sizeof(double));
+    }
+  }
+  m->launches += 2;
   RUN(launch_cast_f32_bf16(feat_i_dev, d.enc_bf16, static_cast<long long>(K) * N, kEncDim, 0, c.st));
   RUN(launch_cast_f32_bf16(feat_j_dev, d.enc_bf16 + static_cast<size_t>(K) * N * kEncDim, static_cast<long long>(K) * N,
                            kEncDim, 0, c.st));
-  RUN(launch_make_positions(d.pos, S, h, w, 1, c.st));
-  RUN(run_decoder(c, K, N, d, nullptr, nullptr));
-  m->launches += 2;
-  RUN(launch_pose_head(d.xd, static_cast<long long>(M) * kDecDim, K, 1, kLnEps, m->pose, pose_out_dev, pose_conf_out_dev,
-                       c.st));
-  RUN(launch_pose_head(d.xd + static_cast<long long>(K) * M * kDecDim, static_cast<long long>(M) * kDecDim, K, 1, kLnEps,
-                       m->pose, pose_out_dev + static_cast<long long>(K) * 16, pose_conf_out_dev + K, c.st));
-  const long long px = static_cast<long long>(H) * W;
-  for (int v = 0; v < 2; ++v) {
-    const size_t save = ws.off;
-    const size_t tok0 = static_cast<size_t>(v) * K * N;
-    RUN(run_dpt(c, ws, K, h, w, d.enc_bf16 + tok0 * 1024, d.hook[0] + tok0 * 768, d.hook[1] + tok0 * 768,
-                d.hook[2] + tok0 * 768, pts3d_out_dev + static_cast<long long>(v) * K * px * 3,
-                conf_out_dev + static_cast<long long>(v) * K * px));
-    ws.off = save;
-  }
-  if (intri_out_dev || depth_out_dev || conf_mean_out_dev) {
-    STA_REQUIRE(scratch != nullptr && intri_out_dev != nullptr,
-                "the pointmap consumers need the scratch buffer and intri_out (depth_out / conf_mean_out are optional)");
-    m->launches += 2;
-    RUN(launch_pointmap_consumers(pts3d_out_dev, conf_out_dev, S, H, W, 2, intri_out_dev, depth_out_dev,
-                                  conf_mean_out_dev, scratch, c.st));
+  auto body = [&](const Ctx& cc) -> int {
+    m->launches += 3;
+    RUN(launch_make_positions(d.pos, S, h, w, 1, cc.st));
+    RUN(run_decoder(cc, K, N, d, nullptr, nullptr));
+    RUN(launch_pose_head(d.xd, static_cast<long long>(M) * kDecDim, K, 1, kLnEps, m->pose, o_pose, o_pconf, cc.st));
+    RUN(launch_pose_head(d.xd + static_cast<long long>(K) * M * kDecDim, static_cast<long long>(M) * kDecDim, K, 1,
+                         kLnEps, m->pose, o_pose + static_cast<long long>(K) * 16, o_pconf + K, cc.st));
+    for (int v = 0; v < 2; ++v) {
+      const size_t save = ws.off;
+      const size_t tok0 = static_cast<size_t>(v) * K * N;
+      RUN(run_dpt(cc, ws, K, h, w, d.enc_bf16 + tok0 * 1024, d.hook[0] + tok0 * 768, d.hook[1] + tok0 * 768,
+                  d.hook[2] + tok0 * 768, o_pts + static_cast<long long>(v) * K * px * 3,
+                  o_conf + static_cast<long long>(v) * K * px));
+      ws.off = save;
+    }
+    if (consumers) {
+      m->launches += 2;
+      RUN(launch_pointmap_consumers(o_pts, o_conf, S, H, W, 2, o_intri, o_depth, o_cmean, o_scratch, cc.st));
+    }
+    return 0;
+  };
+  if (!graphed) return body(c);
+  RUN(run_graphed(m, c.st, {2, K, H, W, consumers ? 1 : 0, depth_out_dev ? 1 : 0, conf_mean_out_dev ? 1 : 0}, body));
+  auto copy = [&](float* dst, const float* src, size_t n) -> int {
+    if (dst) STA_CHECK_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+    return 0;
+  };
+  RUN(copy(pose_out_dev, o_pose, static_cast<size_t>(S) * 16));
+  RUN(copy(pose_conf_out_dev, o_pconf, S));
+  RUN(copy(pts3d_out_dev, o_pts, static_cast<size_t>(S) * px * 3));
+  RUN(copy(conf_out_dev, o_conf, static_cast<size_t>(S) * px));
+  if (consumers) {
+    RUN(copy(intri_out_dev, o_intri, static_cast<size_t>(K) * 9));
+    RUN(copy(depth_out_dev, o_depth, static_cast<size_t>(S) * px));
+    RUN(copy(conf_mean_out_dev, o_cmean, S));
   }
   return 0;
 }
@@ -1287,6 +1436,8 @@ int sta_op_gemm(const StaGemmDesc* d, void* stream) {
   g.lda = d->lda;
   g.Wt = static_cast<const bf16*>(d->W);
   g.ldw = d->ldw;
+  g.splitk_ws = d->splitk_ws;
+  g.splitk_ws_bytes = d->splitk_ws ? static_cast<size_t>(d->splitk_ws_bytes) : 0;
   GemmParams p = {};
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.nimg = d->nimg; p.H = d->H; p.W = d->Wd; p.Cin = d->Cin;
