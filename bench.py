@@ -263,10 +263,12 @@ def run_b200_arm(args, rank, local_rank, world):
     roofline = {
         "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM 3x3 conv family)",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        # DRAM bytes per launch: mean over the 4 consecutive gemm_tc_kernel launches of one ncu --set full capture
-        # (profiles/r01_ncu_gemm_full_summary.txt; read+write 142 / 278 / 104 / 136 MB, equal to the operand + output
-        # sizes of those launches, i.e. no re-reads); the family is tensor-bound, so this is context, not the bound
-        "traffic": 165.0e6, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+        # DRAM bytes per launch: mean over four consecutive gemm_tc_kernel launches (one encoder block: qkv+RoPE,
+        # proj+residual, fc1+GELU, fc2+residual) of one `ncu --set full` capture of a timed cfg-2 forward
+        # (profiles/r01_ncu_gemm_full_summary.txt: read+write 156 / 196 / 207 / 388 MB against 207 / 253 / 260 / 411 MB of
+        # operands + outputs, i.e. no re-reads; tensor pipe active 86-88 % on three of them, 57 % on the HBM-limited
+        # K = 1024 residual projection); the family is tensor-bound, so this is context, not the bound
+        "traffic": 237.0e6, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
         "peak_source": peaks["source"] + ", sustained cuBLAS bf16 (kernel timed inside a long step)",
         "launches_per_step": int(gemm_launches), "avg_launch_ms": gemm_ms / max(1, gemm_launches),
         "algorithmic_gflop_per_launch_avg": P * gemm_flops_pair / max(1, gemm_launches) / 1e9,

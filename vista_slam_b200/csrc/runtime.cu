@@ -185,7 +185,7 @@ struct StaModel {
   size_t io_bytes = 0;
   static constexpr int kMaxHostChunks = 32;
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the host entry point
-  cudaEvent_t ev_in[kMaxHostChunks] = {}, ev_done[kMaxHostChunks] = {}, ev_v1[kMaxHostChunks] = {}, ev_start = nullptr;
+  cudaEvent_t ev_in[kMaxHostChunks] = {}, ev_done[kMaxHostChunks] = {}, ev_part[kMaxHostChunks][4] = {}, ev_start = nullptr;
   int64_t launches = 0;
   int max_pairs_per_chunk = 16;
 
@@ -886,7 +886,7 @@ int check_ready(StaModel* m) {
 
 int forward_chunk(const Ctx& c, const void* img1, const void* img2, int img_is_bf16, int B, int H, int W,
                   float* pts3d, float* conf, float* pose, float* pose_conf, int B_total,
-                  cudaEvent_t ev_view1_done = nullptr) {
+                  cudaEvent_t* ev_parts = nullptr) {
   StaModel* m = c.m;
   const int h = H / 16, w = W / 16, N = h * w, S = 2 * B, M = N + 1;
   RUN(ensure_ws(m, S, h, w));
@@ -912,17 +912,22 @@ int forward_chunk(const Ctx& c, const void* img1, const void* img2, int img_is_b
     RUN(launch_pose_head(d.xd + static_cast<long long>(B) * M * kDecDim, static_cast<long long>(M) * kDecDim, B, 1,
                          kLnEps, m->pose, pose + static_cast<long long>(B_total) * 16, pose_conf + B_total, c.st));
   }
-  // DPT heads: view 1 images then view 2 images (outputs are [2][B_total] blocks)
+  // DPT heads: view 1 images then view 2 images (outputs are [2][B_total] blocks).  The host entry point passes four
+  // events: each view is then processed in two halves and an event is recorded after every part, so that the D2H copy
+  // of one part runs under the head of the next and only the last quarter of the outputs is exposed.
   const long long px = static_cast<long long>(H) * W;
+  const int halves = (ev_parts && B >= 2) ? 2 : 1;
   for (int v = 0; v < 2; ++v) {
-    const size_t save = ws.off;
-    const size_t tok0 = static_cast<size_t>(v) * B * N;
-    RUN(run_dpt(c, ws, B, h, w, d.enc_bf16 + tok0 * 1024, d.hook[0] + tok0 * 768, d.hook[1] + tok0 * 768,
-                d.hook[2] + tok0 * 768, pts3d + static_cast<long long>(v) * B_total * px * 3,
-                conf + static_cast<long long>(v) * B_total * px));
-    ws.off = save;
-    // view 1's pointmaps are final: the host entry point starts their D2H copy under view 2's head
-    if (v == 0 && ev_view1_done) STA_CHECK_CUDA(cudaEventRecord(ev_view1_done, c.st));
+    for (int hf = 0; hf < halves; ++hf) {
+      const int i0 = hf * (B / halves), nb = (hf == halves - 1) ? B - i0 : B / halves;
+      const size_t save = ws.off;
+      const size_t tok0 = (static_cast<size_t>(v) * B + i0) * N;
+      RUN(run_dpt(c, ws, nb, h, w, d.enc_bf16 + tok0 * 1024, d.hook[0] + tok0 * 768, d.hook[1] + tok0 * 768,
+                  d.hook[2] + tok0 * 768, pts3d + (static_cast<long long>(v) * B_total + i0) * px * 3,
+                  conf + (static_cast<long long>(v) * B_total + i0) * px));
+      ws.off = save;
+      if (ev_parts) STA_CHECK_CUDA(cudaEventRecord(ev_parts[v * 2 + hf], c.st));
+    }
   }
   return 0;
 }
@@ -999,7 +1004,7 @@ void sta_destroy(StaModel* m) {
     for (int i = 0; i < StaModel::kMaxHostChunks; ++i) {
       cudaEventDestroy(m->ev_in[i]);
       cudaEventDestroy(m->ev_done[i]);
-      cudaEventDestroy(m->ev_v1[i]);
+      for (int k = 0; k < 4; ++k) cudaEventDestroy(m->ev_part[i][k]);
     }
     cudaEventDestroy(m->ev_start);
   }
@@ -1356,7 +1361,7 @@ int sta_forward_pairs_host(StaModel* m, const void* img1_host, const void* img2_
     for (int i = 0; i < StaModel::kMaxHostChunks; ++i) {
       STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming));
       STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
-      STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_v1[i], cudaEventDisableTiming));
+      for (int k = 0; k < 4; ++k) STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_part[i][k], cudaEventDisableTiming));
     }
     STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
   }
@@ -1370,7 +1375,17 @@ int sta_forward_pairs_host(StaModel* m, const void* img1_host, const void* img2_
 
   // Pipeline over chunks of pairs: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the compute
   // of chunk c (separate copy streams, pinned host memory makes them truly asynchronous).
-  int cp = (B >= 16) ? 8 : B;
+  // one chunk of up to 16 pairs measured best on B200 (448 vs 433 pairs/s for two chunks of 8 at B = 16: the exposed
+  // H2D of a 16-pair chunk costs less than running the GEMMs at half the tile count); larger batches pipeline chunks
+  int cp = B;
+  {
+    static int chunk_env = -1;  // STA_HOST_CHUNK=n overrides the pairs per pipelined chunk (tuning knob)
+    if (chunk_env < 0) {
+      const char* e = getenv("STA_HOST_CHUNK");
+      chunk_env = e ? atoi(e) : 0;
+    }
+    if (chunk_env > 0) cp = chunk_env < B ? chunk_env : B;
+  }
   if (cp > m->max_pairs_per_chunk) cp = m->max_pairs_per_chunk;
   int nchunks = (B + cp - 1) / cp;
   if (nchunks > StaModel::kMaxHostChunks) {
@@ -1398,16 +1413,21 @@ int sta_forward_pairs_host(StaModel* m, const void* img1_host, const void* img2_
     STA_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_in[c], 0));
     RUN(forward_chunk(cx, d_img1 + b0 * img_pair, d_img2 + b0 * img_pair, img_is_bf16, nb, H, W,
                       d_pts + static_cast<size_t>(b0) * px * 3, d_conf + static_cast<size_t>(b0) * px,
-                      d_pose + static_cast<size_t>(b0) * 16, d_pconf + b0, B, m->ev_v1[c]));
+                      d_pose + static_cast<size_t>(b0) * 16, d_pconf + b0, B, m->ev_part[c]));
     STA_CHECK_CUDA(cudaEventRecord(m->ev_done[c], st));
+    const int halves = nb >= 2 ? 2 : 1;  // must mirror forward_chunk
     for (int v = 0; v < 2; ++v) {
-      STA_CHECK_CUDA(cudaStreamWaitEvent(m->s_out, v == 0 ? m->ev_v1[c] : m->ev_done[c], 0));
-      const size_t o = static_cast<size_t>(v) * B + b0;
-      STA_CHECK_CUDA(cudaMemcpyAsync(pts3d_out_host + o * px * 3, d_pts + o * px * 3, nb * px * 3 * sizeof(float),
-                                     cudaMemcpyDeviceToHost, m->s_out));
-      STA_CHECK_CUDA(cudaMemcpyAsync(conf_out_host + o * px, d_conf + o * px, nb * px * sizeof(float),
-                                     cudaMemcpyDeviceToHost, m->s_out));
+      for (int hf = 0; hf < halves; ++hf) {
+        const int i0 = hf * (nb / halves), ni = (hf == halves - 1) ? nb - i0 : nb / halves;
+        STA_CHECK_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_part[c][v * 2 + hf], 0));
+        const size_t o = static_cast<size_t>(v) * B + b0 + i0;
+        STA_CHECK_CUDA(cudaMemcpyAsync(pts3d_out_host + o * px * 3, d_pts + o * px * 3, ni * px * 3 * sizeof(float),
+                                       cudaMemcpyDeviceToHost, m->s_out));
+        STA_CHECK_CUDA(cudaMemcpyAsync(conf_out_host + o * px, d_conf + o * px, ni * px * sizeof(float),
+                                       cudaMemcpyDeviceToHost, m->s_out));
+      }
     }
+    STA_CHECK_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_done[c], 0));
     for (int v = 0; v < 2; ++v) {
       const size_t o = static_cast<size_t>(v) * B + b0;
       STA_CHECK_CUDA(cudaMemcpyAsync(pose_out_host + o * 16, d_pose + o * 16, nb * 16 * sizeof(float),
