@@ -191,6 +191,20 @@ int sta_pointmap_consumers(const float* pts3d, const float* conf, int V, int H, 
 int sta_depth_scale(const float* Di, const float* Dj, const float* ci, const float* cj, int64_t n, float* out2,
                     void* scratch, void* stream);
 
+
+/* ---- image preprocessing: SLAM_image_only.process_image
+ * (vista_slam/datasets/slam_images_only.py:22-34 -> datasets/base/base_view_graph_dataset.py:171-225 ->
+ * utils/cropping.py:54-84,102-118 with PIL LANCZOS -> utils/image.py:13) on the device, bit-exact with PIL's 8-bit
+ * resampler and torchvision's ToTensor / Normalize(0.5, 0.5) / Grayscale.  rgb [H][W][3] uint8 (RGB order) on the
+ * device; res_w >= res_h is the dataset `resolution` (portrait frames get the transposed one, as in the reference).
+ * Outputs: rgb_out [3][oh][ow] fp32 in [-1, 1] (the STA input), gray_out [oh][ow] fp32 in [0, 1] or NULL,
+ * u8_out [oh][ow][3] (the resized crop itself) or NULL.  sta_preprocess_shape returns (oh, ow) without touching
+ * the GPU.  Coefficient tables and the intermediate image are cached per (device, frame geometry); calls for one
+ * geometry must not overlap on different streams. ---- */
+int sta_preprocess_shape(int H, int W, int res_w, int res_h, int w_edge, int h_edge, int* out_hw);
+int sta_preprocess_rgb8(const uint8_t* rgb_dev, int H, int W, int res_w, int res_h, int w_edge, int h_edge,
+                        float* rgb_out_dev, float* gray_out_dev, uint8_t* u8_out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

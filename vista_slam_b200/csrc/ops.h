@@ -57,6 +57,10 @@ int launch_fill_pose_token(float* x, const float* tok, int samples, int tokens_p
                            cudaStream_t stream);
 int launch_upsample2x(const bf16* in, bf16* out, int nimg, int H, int W, int C, int OH, int OW, cudaStream_t stream);
 int launch_rope2d(bf16* tokens, const long long* pos, int B, int N, int H, cudaStream_t stream);
+// preprocess.cu: SLAM_image_only.process_image on the device (PIL-exact Lanczos resize + ToTensor/Normalize/Grayscale)
+int launch_preprocess_rgb8(const uint8_t* rgb_dev, int H, int W, int res_w, int res_h, int w_edge, int h_edge,
+                           float* rgb_out, float* gray_out, uint8_t* u8_out, int* out_hw_host, int query_only,
+                           cudaStream_t stream);
 // pointmap.cu: reductions over the head outputs (slam_utils.py:8-79,168-190)
 size_t pointmap_scratch_bytes(int V);
 int launch_pointmap_consumers(const float* pts3d, const float* conf, int V, int H, int W, int shared, float* K_out,

@@ -1535,4 +1535,16 @@ int sta_depth_scale(const float* Di, const float* Dj, const float* ci, const flo
   return launch_depth_scale(Di, Dj, ci, cj, static_cast<long long>(n), out2, scratch, static_cast<cudaStream_t>(stream));
 }
 
+// ---------------------------------------------------------------------------
+// image preprocessing (preprocess.cu)
+// ---------------------------------------------------------------------------
+int sta_preprocess_shape(int H, int W, int res_w, int res_h, int w_edge, int h_edge, int* out_hw) {
+  return launch_preprocess_rgb8(nullptr, H, W, res_w, res_h, w_edge, h_edge, nullptr, nullptr, nullptr, out_hw, 1, nullptr);
+}
+int sta_preprocess_rgb8(const uint8_t* rgb_dev, int H, int W, int res_w, int res_h, int w_edge, int h_edge,
+                        float* rgb_out_dev, float* gray_out_dev, uint8_t* u8_out_dev, void* stream) {
+  return launch_preprocess_rgb8(rgb_dev, H, W, res_w, res_h, w_edge, h_edge, rgb_out_dev, gray_out_dev, u8_out_dev,
+                                nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"
