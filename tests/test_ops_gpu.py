@@ -42,7 +42,7 @@ def test_implicit_gemm_conv_and_head(capsys):
 
 
 def test_attention_self_and_cross(capsys):
-    assert len(_collect(bu.group_attention, capsys)) == 11
+    assert len(_collect(bu.group_attention, capsys)) == 12
 
 
 def test_bandwidth_kernels(capsys):

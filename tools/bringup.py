@@ -270,6 +270,21 @@ def group_attention():
             k, v = k[idx], v[idx]
         ref = F.scaled_dot_product_attention(q, k, v, scale=0.125).transpose(1, 2).reshape(batch, n, C)
         report("attention b%d h%d n%d shift%d split%d" % (batch, heads, n, shift, split), out, ref, 2e-2)
+    # adversarial for the lazy-rescale / speculative-maximum path: the keys of later tiles score much higher than those
+    # of earlier ones (row maxima jump by far more than 2^8 between key tiles), some rows only in the ragged last tile
+    batch, heads, n = 2, 3, 600
+    C = heads * 64
+    qkv = torch.randn(batch, n, 3 * C, device=dev)
+    growth = 1.0 + 5.0 * (torch.arange(n, device=dev) // 128).float()           # key tile t scaled by 1 + 5t
+    qkv[:, :, C:2 * C] *= growth[None, :, None]
+    qkv[0, 590:, C:2 * C] *= 4.0                                                  # a further jump inside the last tile
+    qkv = qkv.bfloat16()
+    out = torch.zeros(batch, n, C, device=dev, dtype=torch.bfloat16)
+    check(L.sta_op_attention(ptr(qkv), 3 * C, 0, ptr(qkv), 3 * C, C, ptr(qkv), 3 * C, 2 * C, ptr(out), C, batch, heads, n, n,
+                             0, 0.125, 0, cur_stream()), "attention")
+    q, k, v = [qkv[..., i * C:(i + 1) * C].float().view(batch, n, heads, 64).transpose(1, 2) for i in range(3)]
+    ref = F.scaled_dot_product_attention(q, k, v, scale=0.125).transpose(1, 2).reshape(batch, n, C)
+    report("attention growing maxima (rescale path)", out, ref, 2e-2)
 
 
 def group_misc():
