@@ -109,11 +109,19 @@ def test_full_size_properties_cfg2(cuda_model):
     for res in (main, sup):
         assert res["pts3d_pred"].shape == (B, H, W, 3) and torch.isfinite(res["pts3d_pred"]).all()
         assert torch.isfinite(res["relative_pose"]).all()
+    again, _ = cuda_model.forward_pairs(i1, i2)
+    assert torch.equal(again["pts3d_pred"], main["pts3d_pred"])         # deterministic kernels (no atomics)
+    # no cross-pair op: a pair's result does not depend on its batch neighbours.  Bit-identical as long as the same
+    # tile route is taken (8 vs 16 pairs); a single pair takes the small-problem route (128-wide tiles, split-K with a
+    # fixed but different fp32 summation order), so it agrees to the bf16 rounding level instead.
+    m8, s8 = cuda_model.forward_pairs(i1[4:12], i2[4:12])
+    assert torch.equal(m8["pts3d_pred"][1], main["pts3d_pred"][5])
+    assert torch.equal(s8["relative_pose"][1], sup["relative_pose"][5])
     m1, s1 = cuda_model.forward_pairs(i1[5:6], i2[5:6])
-    assert torch.equal(m1["pts3d_pred"][0], main["pts3d_pred"][5])      # deterministic kernels, no cross-pair op
-    assert torch.equal(s1["relative_pose"][0], sup["relative_pose"][5])
-    m2, s2 = cuda_model.forward_pairs(i2[:2], i1[:2])                    # swapped views
-    assert torch.equal(m2["pts3d_pred"], sup["pts3d_pred"][:2]) and torch.equal(s2["conf"], main["conf"][:2])
+    assert maxn(m1["pts3d_pred"][0], main["pts3d_pred"][5]) < 2e-2
+    assert maxn(s1["relative_pose"][0], sup["relative_pose"][5]) < 5e-3
+    m2, s2 = cuda_model.forward_pairs(i2, i1)                             # swapped views
+    assert torch.equal(m2["pts3d_pred"], sup["pts3d_pred"]) and torch.equal(s2["conf"], main["conf"])
 
 
 def test_host_entry_point_matches_device_entry_point(cuda_model):

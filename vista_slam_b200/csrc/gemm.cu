@@ -74,16 +74,6 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
 
   // BN = 256 for the wide trunk layers, 128 when N is not a multiple of 256.
   int bn = (p.N % 256 == 0 && g.epi != EPI_PIXSHUF && g.epi != EPI_HEAD) ? 256 : 128;
-  {
-    // experiment knob: STA_GEMM_BN128_MAXN=n uses 128-wide tiles for N <= n (finer wave quantisation)
-    static int maxn = -1;
-    if (maxn < 0) {
-      const char* e = getenv("STA_GEMM_BN128_MAXN");
-      maxn = e ? atoi(e) : 0;
-    }
-    if (bn == 256 && p.N <= maxn && (g.epi == EPI_BF16 || g.epi == EPI_F32) && g.amode == A_LINEAR) bn = 128;
-  }
-
   int cg = cta_group_mode();
 
   // TMA-store epilogue (epilogue_tile_tma) for the wide linear layers: bf16 / GELU / RoPE outputs without skip
