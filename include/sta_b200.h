@@ -202,6 +202,11 @@ int sta_depth_scale(const float* Di, const float* Dj, const float* ci, const flo
  * the GPU.  Coefficient tables and the intermediate image are cached per (device, frame geometry); calls for one
  * geometry must not overlap on different streams. ---- */
 int sta_preprocess_shape(int H, int W, int res_w, int res_h, int w_edge, int h_edge, int* out_hw);
+/* Host-only test hooks (no GPU): the crop/resize geometry {crop l, t, r, b, resized w, h, final l, t, out w, h} and
+ * the fixed-point Lanczos windows of one axis (Resample.c precompute_coeffs + normalize_coeffs_8bpc): *ksize taps per
+ * output sample, bounds [out_size][2] = (first input sample, tap count), kk [out_size][*ksize] int32 (22-bit). */
+int sta_preprocess_geometry(int H, int W, int res_w, int res_h, int w_edge, int h_edge, int* out10);
+int sta_preprocess_coeffs(int in_size, int out_size, int* ksize, int* bounds, int* kk, int64_t kk_capacity);
 int sta_preprocess_rgb8(const uint8_t* rgb_dev, int H, int W, int res_w, int res_h, int w_edge, int h_edge,
                         float* rgb_out_dev, float* gray_out_dev, uint8_t* u8_out_dev, void* stream);
 

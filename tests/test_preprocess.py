@@ -43,6 +43,41 @@ def test_shape_query_and_no_cpu_path():
         ds.process_image(np.zeros((480, 640, 3), dtype=np.uint8))
 
 
+def test_host_geometry_and_coefficient_tables_match_oracle_exactly():
+    """The library's host side (crop geometry, PIL coefficient windows in double precision) against the oracle over
+    many frame sizes -- no GPU needed: these tables are all the kernels consume besides the pixels."""
+    import ctypes
+    from vista_slam_b200 import _lib
+    L = _lib.lib()
+    rs = np.random.RandomState(5)
+    sizes = [(480, 640), (720, 1280), (1280, 720), (1080, 1920), (357, 491), (150, 200), (244, 500), (468, 468)]
+    sizes += [(int(rs.randint(120, 1400)), int(rs.randint(120, 2000))) for _ in range(60)]
+    checked = 0
+    for (H, W) in sizes:
+        for res in ((224, 224), (512, 384)):
+            try:
+                g = orc.crop_resize_geometry(H, W, res)
+            except (NotImplementedError, AssertionError):
+                out = (ctypes.c_int * 10)()
+                assert L.sta_preprocess_geometry(H, W, res[0], res[1], 10, 10, out) != 0   # refused alike
+                continue
+            out = (ctypes.c_int * 10)()
+            _lib.check(L.sta_preprocess_geometry(H, W, res[0], res[1], 10, 10, out))
+            assert tuple(out) == g["crop"] + g["resized"] + g["final"] + tuple(int(v) for v in g["out"]), (H, W, res)
+            l, t, r, b = g["crop"]
+            for in_size, out_size in ((r - l, g["resized"][0]), (b - t, g["resized"][1])):
+                ksize, bounds, kk = orc.precompute_coeffs_8bpc(in_size, out_size)
+                cb = (ctypes.c_int * (2 * out_size))()
+                ck = (ctypes.c_int * (out_size * ksize))()
+                cks = ctypes.c_int()
+                _lib.check(L.sta_preprocess_coeffs(in_size, out_size, ctypes.byref(cks), cb, ck, out_size * ksize))
+                assert cks.value == ksize
+                assert np.array_equal(np.frombuffer(cb, dtype=np.int32).reshape(out_size, 2), bounds)
+                assert np.array_equal(np.frombuffer(ck, dtype=np.int32).reshape(out_size, ksize), kk), (in_size, out_size)
+                checked += 1
+    assert checked > 100
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", CASES)
 def test_kernels_are_bit_exact_with_reference_golden(case):

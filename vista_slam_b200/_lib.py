@@ -81,6 +81,8 @@ def lib():
     L.sta_op_cast_f32_bf16.argtypes = [vp, vp, i64, i, i, vp]
     L.sta_op_rope2d.argtypes = [vp, vp, i, i, i, vp]
     L.sta_preprocess_shape.argtypes = [i, i, i, i, i, i, POINTER(c_int)]
+    L.sta_preprocess_geometry.argtypes = [i, i, i, i, i, i, POINTER(c_int)]
+    L.sta_preprocess_coeffs.argtypes = [i, i, POINTER(c_int), POINTER(c_int), POINTER(c_int), i64]
     L.sta_preprocess_rgb8.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, vp]
     L.sta_pointmap_scratch_bytes.argtypes = [i]
     L.sta_pointmap_scratch_bytes.restype = ctypes.c_size_t

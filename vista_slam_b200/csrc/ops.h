@@ -61,6 +61,8 @@ int launch_rope2d(bf16* tokens, const long long* pos, int B, int N, int H, cudaS
 int launch_preprocess_rgb8(const uint8_t* rgb_dev, int H, int W, int res_w, int res_h, int w_edge, int h_edge,
                            float* rgb_out, float* gray_out, uint8_t* u8_out, int* out_hw_host, int query_only,
                            cudaStream_t stream);
+int preprocess_geometry(int H, int W, int res_w, int res_h, int w_edge, int h_edge, int* out10);
+int preprocess_coeffs(int in_size, int out_size, int* ksize_out, int* bounds_out, int* kk_out, long long kk_capacity);
 // pointmap.cu: reductions over the head outputs (slam_utils.py:8-79,168-190)
 size_t pointmap_scratch_bytes(int V);
 int launch_pointmap_consumers(const float* pts3d, const float* conf, int V, int H, int W, int shared, float* K_out,

@@ -230,6 +230,26 @@ int get_plan(int H, int W, int res_w, int res_h, int w_edge, int h_edge, const P
 
 }  // namespace
 
+// host-only test hooks (no GPU work): the geometry and the PIL coefficient windows the kernels are driven by
+int preprocess_geometry(int H, int W, int res_w, int res_h, int w_edge, int h_edge, int* out10) {
+  Geometry g;
+  if (int rc = make_geometry(H, W, res_w, res_h, w_edge, h_edge, &g)) return rc;
+  const int v[10] = {g.l, g.t, g.l + g.W1, g.t + g.H1, g.rw, g.rh, g.l2, g.t2, g.ow, g.oh};
+  for (int i = 0; i < 10; ++i) out10[i] = v[i];
+  return 0;
+}
+int preprocess_coeffs(int in_size, int out_size, int* ksize_out, int* bounds_out, int* kk_out, long long kk_capacity) {
+  STA_REQUIRE(in_size > 0 && out_size > 0 && ksize_out && bounds_out && kk_out, "bad arguments");
+  int ksize = 0;
+  std::vector<int> b, k;
+  precompute_coeffs(in_size, out_size, &ksize, &b, &k);
+  STA_REQUIRE(static_cast<long long>(k.size()) <= kk_capacity, "coefficient buffer too small");
+  *ksize_out = ksize;
+  for (size_t i = 0; i < b.size(); ++i) bounds_out[i] = b[i];
+  for (size_t i = 0; i < k.size(); ++i) kk_out[i] = k[i];
+  return 0;
+}
+
 int launch_preprocess_rgb8(const uint8_t* rgb_dev, int H, int W, int res_w, int res_h, int w_edge, int h_edge,
                            float* rgb_out, float* gray_out, uint8_t* u8_out, int* out_hw_host, int query_only,
                            cudaStream_t stream) {

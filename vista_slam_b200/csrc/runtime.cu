@@ -1541,6 +1541,16 @@ int sta_depth_scale(const float* Di, const float* Dj, const float* ci, const flo
 int sta_preprocess_shape(int H, int W, int res_w, int res_h, int w_edge, int h_edge, int* out_hw) {
   return launch_preprocess_rgb8(nullptr, H, W, res_w, res_h, w_edge, h_edge, nullptr, nullptr, nullptr, out_hw, 1, nullptr);
 }
+int sta_preprocess_geometry(int H, int W, int res_w, int res_h, int w_edge, int h_edge, int* out10) {
+  if (!out10) {
+    set_last_error("sta_preprocess_geometry: null output");
+    return 2;
+  }
+  return preprocess_geometry(H, W, res_w, res_h, w_edge, h_edge, out10);
+}
+int sta_preprocess_coeffs(int in_size, int out_size, int* ksize, int* bounds, int* kk, int64_t kk_capacity) {
+  return preprocess_coeffs(in_size, out_size, ksize, bounds, kk, static_cast<long long>(kk_capacity));
+}
 int sta_preprocess_rgb8(const uint8_t* rgb_dev, int H, int W, int res_w, int res_h, int w_edge, int h_edge,
                         float* rgb_out_dev, float* gray_out_dev, uint8_t* u8_out_dev, void* stream) {
   return launch_preprocess_rgb8(rgb_dev, H, W, res_w, res_h, w_edge, h_edge, rgb_out_dev, gray_out_dev, u8_out_dev,
