@@ -49,6 +49,7 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 struct AttnParams {
   int nq, nk, batch, heads, qpairs, kv_batch_shift;
   int nitems;
+  int pingpong;  // enforce alternating exp2 phases of the two softmax groups
   int q_row0;  // first query row handled by the tiled kernel (1 when row 0 goes to attention_row0_kernel)
   float scale_log2;
   __nv_bfloat16* out;
@@ -236,7 +237,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tO = tmem_base + lane_addr + 256 + grp * 64;  // this group's O accumulator
     uint8_t* prow = sP + grp * 2 * TILE_BYTES + r * 128;         // this group's P buffer, row r
     int n = 0;  // key-tile step counter (barrier parities)
-
+    // Enforced ping-pong of the MUFU-bound phase (STA_ATTN_PINGPONG, default on): the two groups take turns with the
+    // exponentials -- group t waits on named barrier 3 + t before its exp2 loop and hands the turn to the other
+    // group right after it -- so that one group's exp2 work overlaps the other's TMEM load / row maximum / P store /
+    // handshake instead of both contending for the same 16 MUFU lanes at the same time.  Both groups run the same
+    // number of key-tile steps, so the turns alternate A, B, A, B, ... for the whole kernel.
+    const bool pingpong = p.pingpong != 0;
+    auto turn_wait = [&]() { if (pingpong) named_bar_sync(3 + grp, 256); };
+    auto turn_pass = [&]() { if (pingpong) named_bar_arrive(3 + (grp ^ 1), 256); };
+    if (pingpong && grp == 1) named_bar_arrive(3, 256);  // group A goes first
 
     for (int it = 0; it < my_items; ++it) {
       int q0, head, b, kvb;
@@ -289,6 +298,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             named_bar_sync(1 + grp, 128);
           }
           float rs = 0.f;
+          turn_wait();
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             float e[8];
@@ -304,6 +314,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             q.w = pack_bf16x2(e[6], e[7]);
             *reinterpret_cast<uint4*>(prow + ((c ^ rx) << 4)) = q;
           }
+          turn_pass();
           l += rs;
           fence_proxy_async_smem();
           tc_fence_before();
@@ -372,6 +383,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         // ---- P = exp2(S*c - m_used) -> bf16, 128B-swizzled K-major tile in this group's P buffer ----
         float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+        turn_wait();
 #pragma unroll
         for (int c = 0; c < 16; ++c) {  // 16-byte chunks of 8 keys
           float e[8];
@@ -388,6 +400,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           q.w = pack_bf16x2(e[6], e[7]);
           *reinterpret_cast<uint4*>(prow + (c >> 3) * TILE_BYTES + (((c & 7) ^ rx) << 4)) = q;
         }
+        turn_pass();
         l += (rs0 + rs1) + (rs2 + rs3);
         fence_proxy_async_smem();
         tc_fence_before();
@@ -422,6 +435,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tma_store_commit();
       }
     }
+    if (pingpong && grp == 0) named_bar_sync(3, 256);  // consume group B's last hand-over
     if (warp == 4 + 4 * grp && lane == 0) tma_store_wait_all();
     tc_fence_before();
   }
@@ -579,6 +593,12 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   p.ldo = a.ldo;
   p.heads = a.heads;
   const size_t row0_smem = (((a.nk + 3) & ~3) + 16 + 32 * 64) * sizeof(float);
+  static int pingpong_env = -1;
+  if (pingpong_env < 0) {
+    const char* e = getenv("STA_ATTN_PINGPONG");  // 0 disables (A/B timing)
+    pingpong_env = (e && e[0] == '0') ? 0 : 1;
+  }
+  p.pingpong = pingpong_env;
   const int split = (a.split_first_row && a.nq > 1 && row0_smem <= 48 * 1024) ? 1 : 0;
   p.q_row0 = split;
   p.qpairs = (a.nq - split + 255) / 256;

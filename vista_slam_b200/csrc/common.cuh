@@ -354,6 +354,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-fabsf(x), ex2_approx(q), fmaxf(x, 0.0f));
 }
 
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
