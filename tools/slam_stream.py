@@ -19,13 +19,11 @@ def main():
     ap.add_argument("--edges", type=int, default=2)
     a = ap.parse_args()
     H, W = [int(v) for v in a.size.split("x")]
-    from oracle.sta_oracle import make_state_dict
     from vista_slam_b200.sta_model.sta_model import SymmetricTwoViewAssociation as STA
     from vista_slam_b200.utils import slam_utils as su
     dev = torch.device("cuda")
-    m = STA()
-    m.load_state_dict(make_state_dict(0), strict=True)
-    m = m.to(dev).eval()
+    torch.manual_seed(0)
+    m = STA().to(dev).eval()   # random-init weights of the reference architecture (timing only)
     g = torch.Generator().manual_seed(1)
     imgs = [(torch.rand(1, 3, H, W, generator=g) * 2 - 1).to(dev) for _ in range(a.keyframes)]
     shape = torch.tensor([[H, W]])
