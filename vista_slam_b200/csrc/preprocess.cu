@@ -208,6 +208,10 @@ int get_plan(int H, int W, int res_w, int res_h, int w_edge, int h_edge, const P
     *out = &it->second;
     return 0;
   }
+  if (plans.size() >= 64) {
+    set_last_error("too many distinct frame geometries (64) for the preprocessing plan cache");
+    return 2;
+  }
   Plan p;
   if (int rc = make_geometry(H, W, res_w, res_h, w_edge, h_edge, &p.g)) return rc;
   std::vector<int> bh, kh, bv, kv;
@@ -220,10 +224,6 @@ int get_plan(int H, int W, int res_w, int res_h, int w_edge, int h_edge, const P
   };
   if (upload(bh, &p.d_bh) || upload(kh, &p.d_kh) || upload(bv, &p.d_bv) || upload(kv, &p.d_kv)) return 1;
   STA_CHECK_CUDA(cudaMalloc(&p.d_tmp, static_cast<size_t>(p.g.H1) * p.g.rw * 3));
-  if (plans.size() >= 64) {
-    set_last_error("too many distinct frame geometries (64) for the preprocessing plan cache");
-    return 2;
-  }
   *out = &plans.emplace(key, p).first->second;
   return 0;
 }
