@@ -33,6 +33,14 @@ int sta_device_synchronize(void);      /* cudaDeviceSynchronize + error check */
 
 /* ---- model lifetime (replaces STA() + load_state_dict + .to(cuda), slam.py:95-106) ---- */
 int sta_create(StaModel** out);
+/* Same with an explicit operand precision.  STA_PRECISION_BF16 (what sta_create uses, and what every benchmark
+ * number is measured with): bf16 tensor-core operands, fp32 accumulation.  STA_PRECISION_X3: split-precision PARITY
+ * mode -- every bf16 activation is carried as (hi | lo | hi) and every bf16 weight as (hi | hi | lo), so the same
+ * tcgen05 kernels compute a_hi w_hi + a_lo w_hi + a_hi w_lo over K' = 3K (about 17 significant operand bits),
+ * and attention runs in fp32 on the CUDA cores.  It exists to check the kernels against the fp32 reference at
+ * north_star's tolerance (pointmaps 1e-3, pose 1e-4); ~3x the weight memory, several times slower. */
+enum { STA_PRECISION_BF16 = 0, STA_PRECISION_X3 = 1 };
+int sta_create_ex(StaModel** out, int precision);
 void sta_destroy(StaModel* m);
 
 /* Upload one state-dict tensor (fp32, contiguous, host or device memory) under its
@@ -135,6 +143,8 @@ typedef struct StaGemmDesc {
   float* conf;          /* EPI_HEAD: [pixels] */
   void* splitk_ws;      /* optional fp32 scratch (16-byte aligned): lets small EPI_F32 problems split K across CTAs */
   int64_t splitk_ws_bytes;
+  int split_precision;  /* 1: operands are already expanded along K as A (hi|lo|hi) x W (hi|hi|lo) (K = 3x logical);
+                           bf16 outputs / skip tensors use (hi|lo|hi) rows of logical width N (ldo >= 3N) */
 } StaGemmDesc;
 
 int sta_op_gemm(const StaGemmDesc* d, void* stream);

@@ -34,3 +34,16 @@ def cuda_model(state_dict):
     m.eval()
     m._ready(torch.empty(1, device="cuda"))
     return m
+
+
+@pytest.fixture(scope="session")
+def cuda_model_x3(state_dict):
+    """The same model in the split-precision parity mode (include/sta_b200.h STA_PRECISION_X3)."""
+    import torch
+    from vista_slam_b200.sta_model.sta_model import SymmetricTwoViewAssociation as STA
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    m = STA(precision="x3")
+    m.load_state_dict(state_dict, strict=True)
+    m.eval()
+    m._ready(torch.empty(1, device="cuda"))
+    return m

@@ -1,11 +1,16 @@
-"""GPU: the whole STA path through the module surface -> C ABI -> sm_100a kernels, against the oracle
-(same seeded inputs) and the golden vectors produced by the unmodified reference.
+"""GPU: the whole STA path through the module surface -> C ABI -> sm_100a kernels, against the golden vectors
+produced by the UNMODIFIED reference (fp32, CPU; tools/make_golden.py) and against the oracle on the same inputs.
 
-Tolerance protocol: bf16 MMA operands cannot meet rtol 1e-3 against an fp32 oracle --
-the reference's own fp32 -> bf16-autocast deviation is 5e-3 (pts3d) / 3.5e-3 (pose), max-normalised.  So:
-  (a) vs the oracle in bf16-operand emulation (same operand precision): tight bounds, stated per output;
-  (b) vs the fp32 reference golden / fp32 oracle: the bf16 noise floor, stated per output.
-Max-normalised error = max|a-b| / max|b|.
+Parity protocol:
+  (1) production precision (bf16 tensor-core operands, fp32 accumulation): bf16 operands cannot meet rtol 1e-3
+      against an fp32 reference, so the bounds are the MEASURED deviations x 2, per output
+      (profiles/r02_parity_report_bf16.json, all four golden cases), for the maximum and the median error, and the
+      deviation from fp32 must be statistically the same as that of the oracle run with the same operand precision
+      (|cuda - fp32| ~ |emu - fp32|): a kernel bug does not hide inside the bf16 noise floor.
+  (2) split-precision parity mode (precision="x3": the same tcgen05 kernels with (hi | lo | hi) x (hi | hi | lo)
+      operands, ~17 significant bits): north_star's tolerance itself -- pointmaps 1e-3, pose 1e-4 -- against the
+      fp32 reference goldens at every size incl. cfg-1 (224x224) and a cfg-2 pair (512x384).
+Max-normalised error = max|a-b| / max|b|; median-normalised = median|a-b| / max|b|.
 """
 import json
 import os
@@ -19,11 +24,19 @@ from oracle.sta_oracle import StaOracle, make_images
 
 pytestmark = pytest.mark.gpu
 
-# Max-normalised bounds, set at ~3x the deviations measured on B200 in round 1 (profiles/r01_model_check*.log:
-# trunk features 6e-3..9e-3, pose 2e-3..1.8e-2, pts3d/conf 1e-2..2e-2 at |xyz| <= 3, pose_conf <= 2e-3).
-# (a) vs oracle-bf16emu, (b) vs fp32 reference golden / fp32 oracle.
-TOL_EMU = {"pts3d_pred": 5e-2, "conf": 5e-2, "relative_pose": 4e-2, "relative_pose_conf": 5e-3}
-TOL_FP32 = {"pts3d_pred": 1e-1, "conf": 1e-1, "relative_pose": 5e-2, "relative_pose_conf": 1e-2}
+KEYS = {"pts3d_pred": "pts3d", "conf": "conf", "relative_pose": "pose", "relative_pose_conf": "pose_conf"}
+CASES = ["pair_64x80", "pair_b2_48x64", "pair_224x224", "pair_384x512"]
+# bf16 production mode: 2 x the largest deviation measured on B200 over the four golden cases and both views
+# (profiles/r02_parity_report_bf16.json): max-normalised measured  vs emu: 1.65e-2 / 1.35e-2 / 1.60e-2 / 2.0e-3,
+# vs fp32 reference: 2.35e-2 / 1.54e-2 / 2.70e-2 / 2.9e-3 (pts3d / conf / pose / pose_conf).
+TOL_EMU = {"pts3d_pred": 3.3e-2, "conf": 2.7e-2, "relative_pose": 3.2e-2, "relative_pose_conf": 4.0e-3}
+TOL_FP32 = {"pts3d_pred": 4.7e-2, "conf": 3.1e-2, "relative_pose": 5.4e-2, "relative_pose_conf": 5.8e-3}
+# median-normalised, dense outputs only (measured <= 1.7e-3 / 1.1e-3)
+TOL_MED_FP32 = {"pts3d_pred": 3.4e-3, "conf": 2.2e-3}
+# trunk features vs the fp32 reference (measured <= 7.8e-3 / 9.7e-3 max, 1.3e-3 / 1.4e-3 median)
+TOL_FEAT = {"enc_feat1": 1.6e-2, "dec": 2.0e-2}
+# north_star: "pointmaps rtol 1e-3, pose params rtol 1e-4" -- met by the split-precision parity mode
+TOL_X3 = {"pts3d_pred": 1e-3, "conf": 1e-3, "relative_pose": 1e-4, "relative_pose_conf": 1e-4}
 
 
 def maxn(a, b):
@@ -31,19 +44,83 @@ def maxn(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("case", ["pair_64x80", "pair_b2_48x64"])
-def test_forward_pairs_vs_oracle_and_reference_golden(cuda_model, state_dict, case):
+def medn(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().median() / b.abs().max().clamp_min(1e-30))
+
+
+def golden_case(case):
     g = np.load(os.path.join(GOLDEN_DIR, case + ".npz"))
     meta = json.loads(str(g["meta"]))
     img1, img2 = make_images(meta["B"], meta["H"], meta["W"], meta["image_seed"])
+    if meta.get("bf16_images"):  # cfg-2 feeds bf16 images; the golden was generated from exactly these values
+        img1, img2 = img1.bfloat16().float(), img2.bfloat16().float()
+    return g, meta, img1, img2
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_forward_pairs_vs_reference_golden_and_oracle(cuda_model, state_dict, case):
+    """Production (bf16) precision on every golden: cfg-1 224x224 and one cfg-2 512x384 pair included."""
+    g, meta, img1, img2 = golden_case(case)
     main, sup = cuda_model.forward_pairs(img1.cuda(), img2.cuda())
     with torch.no_grad():
         o_main, o_sup = StaOracle(state_dict, emulate_bf16=True).forward_pair(img1, img2)
-    gk = {"pts3d_pred": "pts3d", "conf": "conf", "relative_pose": "pose", "relative_pose_conf": "pose_conf"}
     for res, orc, pre in ((main, o_main, "main_"), (sup, o_sup, "support_")):
-        for k in TOL_EMU:
-            assert maxn(res[k], orc[k]) < TOL_EMU[k], (pre, k, maxn(res[k], orc[k]))
-            assert maxn(res[k], torch.from_numpy(g[pre + gk[k]])) < TOL_FP32[k], (pre, k)
+        for k, gk in KEYS.items():
+            gold = torch.from_numpy(g[pre + gk])
+            e_emu, e_fp32 = maxn(res[k], orc[k]), maxn(res[k], gold)
+            assert e_emu < TOL_EMU[k], (pre, k, e_emu)
+            assert e_fp32 < TOL_FP32[k], (pre, k, e_fp32)
+            if k in TOL_MED_FP32:
+                # dense outputs: the deviation from fp32 is the operand-precision noise floor, not more --
+                # compare with what the oracle shows at the same operand precision (max and median)
+                assert medn(res[k], gold) < TOL_MED_FP32[k], (pre, k)
+                assert e_fp32 < 1.6 * maxn(orc[k], gold) + 1e-4, (pre, k, e_fp32, maxn(orc[k], gold))
+                assert medn(res[k], gold) < 1.25 * medn(orc[k], gold) + 1e-5, (pre, k)
+
+
+def test_cfg2_batch16_pair0_is_the_golden_pair(cuda_model):
+    """cfg-2 proper: 16 bf16 512x384 pairs in one call -- the 256-wide CTA-pair GEMM route, 7-tile decoder attention,
+    full DPT pyramid -- with pair 0 = the pair the unmodified reference was run on."""
+    g, meta, img1, img2 = golden_case("pair_384x512")
+    H, W = meta["H"], meta["W"]
+    o1, o2 = make_images(15, H, W, 99)
+    b1 = torch.cat([img1, o1]).bfloat16().cuda()
+    b2 = torch.cat([img2, o2]).bfloat16().cuda()
+    main, sup = cuda_model.forward_pairs(b1, b2)
+    for res, pre in ((main, "main_"), (sup, "support_")):
+        for k, gk in KEYS.items():
+            gold = torch.from_numpy(g[pre + gk])
+            assert maxn(res[k][:1], gold) < TOL_FP32[k], (pre, k, maxn(res[k][:1], gold))
+            if k in TOL_MED_FP32:
+                assert medn(res[k][:1], gold) < TOL_MED_FP32[k], (pre, k)
+    # and the pair's result does not depend on its batch neighbours (same tile route at 8 pairs: bit-identical)
+    m8, s8 = cuda_model.forward_pairs(b1[:8], b2[:8])
+    assert torch.equal(m8["pts3d_pred"][0], main["pts3d_pred"][0]) and torch.equal(s8["relative_pose"][0], sup["relative_pose"][0])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_split_precision_mode_meets_north_star_tolerance(cuda_model_x3, case):
+    """precision='x3' (the same tensor-core kernels, ~17-bit operands) vs the fp32 reference golden:
+    pointmaps 1e-3, pose 1e-4 (BASELINE.json north_star), at every size incl. cfg-1 and a cfg-2 pair."""
+    g, meta, img1, img2 = golden_case(case)
+    main, sup = cuda_model_x3.forward_pairs(img1.cuda(), img2.cuda())
+    for res, pre in ((main, "main_"), (sup, "support_")):
+        for k, gk in KEYS.items():
+            gold = torch.from_numpy(g[pre + gk])
+            e = maxn(res[k], gold)
+            assert e < TOL_X3[k], (case, pre, k, e)
+    # elementwise, the way the survey measured the reference's own bf16 deviation (SURVEY.md App. D)
+    gold = torch.from_numpy(g["main_pts3d"])
+    assert torch.allclose(main["pts3d_pred"].cpu(), gold, rtol=1e-3, atol=1e-3 * float(gold.abs().max()) * 1e-1)
+    # trunk features through the reference-shaped sub-entry points
+    B, H, W = meta["B"], meta["H"], meta["W"]
+    ts = torch.tensor([[H, W]] * B)
+    f1, p1 = cuda_model_x3._encode_image(img1.cuda(), ts, normalize=False)
+    f2, p2 = cuda_model_x3._encode_image(img2.cuda(), ts, normalize=False)
+    d1, _ = cuda_model_x3._decode_stereo(f1, f2, p1, p2, layers=(12,))
+    assert maxn(f1, torch.from_numpy(g["enc_feat1"])) < 1e-3
+    assert maxn(d1[12], torch.from_numpy(g["dec1_12"])) < 1e-3
 
 
 def test_sub_entry_points_match_reference_golden_and_fused_path(cuda_model):
@@ -57,11 +134,11 @@ def test_sub_entry_points_match_reference_golden_and_fused_path(cuda_model):
     f2, p2 = cuda_model._encode_image(img2.cuda(), ts, normalize=False)
     assert f1.shape == (B, (H // 16) * (W // 16), 1024) and p1.dtype == torch.int64
     assert torch.equal(p1.cpu(), torch.from_numpy(g["pos1"]))
-    assert maxn(f1, torch.from_numpy(g["enc_feat1"])) < 5e-2
+    assert maxn(f1, torch.from_numpy(g["enc_feat1"])) < TOL_FEAT["enc_feat1"]
     d1, d2 = cuda_model._decode_stereo(f1, f2, p1, p2)
     assert len(d1) == 13 and len(d2) == 13 and d1[0].shape == (B, (H // 16) * (W // 16) + 1, 768)
     for k, t in (("dec1_6", d1[6]), ("dec1_9", d1[9]), ("dec1_12", d1[12]), ("dec2_12", d2[12])):
-        assert maxn(t, torch.from_numpy(g[k])) < 5e-2, k
+        assert maxn(t, torch.from_numpy(g[k])) < TOL_FEAT["dec"], k
     pts = cuda_model.head_pts([f1] + [t[:, 1:, :] for t in d1], ts)
     pose = cuda_model.head_pose_s(d1[-1][:, 0, :])
     main, _ = cuda_model.forward_pairs(img1.cuda(), img2.cuda())
@@ -73,16 +150,6 @@ def test_sub_entry_points_match_reference_golden_and_fused_path(cuda_model):
     assert set(out) == {"main_views", "support_views"}
     assert set(out["main_views"][0]) == {"pts3d_pred", "conf", "relative_pose", "relative_pose_conf"}
     assert out["main_views"][0]["pts3d_pred"].shape == (B, H, W, 3)
-
-
-def test_cfg1_single_224_pair_vs_oracle(cuda_model, state_dict):
-    img1, img2 = make_images(1, 224, 224, 1234)
-    main, sup = cuda_model.forward_pairs(img1.cuda(), img2.cuda())
-    with torch.no_grad():
-        o_main, o_sup = StaOracle(state_dict, emulate_bf16=True).forward_pair(img1, img2)
-    for res, orc in ((main, o_main), (sup, o_sup)):
-        for k in TOL_EMU:
-            assert maxn(res[k], orc[k]) < TOL_EMU[k], (k, maxn(res[k], orc[k]))
 
 
 def test_pose_is_a_rigid_transform(cuda_model):

@@ -49,6 +49,12 @@ def test_bandwidth_kernels(capsys):
     assert len(_collect(bu.group_misc, capsys)) == 11
 
 
+def test_split_precision_mode_of_the_tensor_core_kernels(capsys):
+    """x3 parity mode at op level: the same tcgen05 GEMM / implicit-conv kernels with (hi | lo | hi) x (hi | hi | lo) operands
+    against fp64 references, 1e-4 max-normalised (100x below the bf16 floor)."""
+    assert len(_collect(bu.group_x3, capsys)) == 13
+
+
 def test_gemm_zero_and_identity_properties():
     """size-independent properties at full cfg-2 size: linearity in the bias and exactness on an identity weight."""
     from vista_slam_b200._lib import EPI_BF16

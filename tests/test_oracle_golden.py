@@ -36,22 +36,27 @@ def _maxn(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("case", ["pair_64x80", "pair_b2_48x64"])
+@pytest.mark.parametrize("case", ["pair_64x80", "pair_b2_48x64", "pair_224x224", "pair_384x512"])
 def test_oracle_fp32_matches_reference_golden(state_dict, case):
+    """incl. cfg-1 (224x224, the reference's native size) and one cfg-2 pair (512x384)."""
     g = np.load(os.path.join(GOLDEN_DIR, case + ".npz"))
     meta = json.loads(str(g["meta"]))
     img1, img2 = make_images(meta["B"], meta["H"], meta["W"], meta["image_seed"])
+    if meta.get("bf16_images"):
+        img1, img2 = img1.bfloat16().float(), img2.bfloat16().float()
     orc = StaOracle(state_dict, emulate_bf16=False)
     with torch.no_grad():
         f1, pos1 = orc.encode_image(img1)
         f2, pos2 = orc.encode_image(img2)
         d1, d2 = orc.decode_stereo(f1, f2, pos1, pos2)
         main, sup = orc.forward_pair(img1, img2)
-    assert torch.equal(pos1, torch.from_numpy(g["pos1"]))
+    if "pos1" in g:
+        assert torch.equal(pos1, torch.from_numpy(g["pos1"]))
     tol = 2e-4  # fp32 summation-order noise through 36 blocks; measured 1e-6 .. 3e-5
     assert _maxn(f1, torch.from_numpy(g["enc_feat1"])) < tol
     for k, t in (("dec1_6", d1[6]), ("dec1_9", d1[9]), ("dec1_12", d1[12]), ("dec2_12", d2[12])):
-        assert _maxn(t, torch.from_numpy(g[k])) < tol, k
+        if k in g:  # the large fixture keeps one feature per stage
+            assert _maxn(t, torch.from_numpy(g[k])) < tol, k
     for pre, res in (("main_", main), ("support_", sup)):
         assert _maxn(res["pts3d_pred"], torch.from_numpy(g[pre + "pts3d"])) < tol
         assert _maxn(res["conf"], torch.from_numpy(g[pre + "conf"])) < tol

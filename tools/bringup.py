@@ -13,7 +13,7 @@ import time
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
-GROUPS = ["gemm_basic", "gemm_epi", "conv", "attention", "misc", "perf"]
+GROUPS = ["gemm_basic", "gemm_epi", "conv", "attention", "misc", "x3", "perf"]
 
 
 def report(name, got, ref, tol):
@@ -345,6 +345,120 @@ def group_misc():
     check(L.sta_op_rope2d(ptr(tok), ptr(pos), 2, 50, 4, st))
     report("rope2d op", tok.view(100, 4, 64), ref, 1e-2)
     torch.cuda.synchronize()
+
+
+def split_act(x):
+    """fp32 [.., C] -> bf16 [.., 3C] = (hi | lo | hi): the activation layout of the split-precision parity mode."""
+    import torch
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    return torch.cat([hi, lo, hi], dim=-1).contiguous()
+
+
+def split_w(w):
+    """fp32 [N, K] -> bf16 [N, 3K] = (hi | hi | lo): the weight layout of the split-precision parity mode."""
+    import torch
+    hi = w.bfloat16()
+    lo = (w - hi.float()).bfloat16()
+    return torch.cat([hi, hi, lo], dim=-1).contiguous()
+
+
+def merge3(o, N, name):
+    """(hi | lo | hi) rows -> fp32 hi + lo; the two hi copies must be identical."""
+    import torch
+    assert torch.equal(o[..., :N], o[..., 2 * N:3 * N]), name + ": hi copies differ"
+    return o[..., :N].float() + o[..., N:2 * N].float()
+
+
+def group_x3():
+    """Split-precision parity mode of the SAME tcgen05 kernels (operands expanded along K, two-pass / three-store
+    epilogues), against fp64 references on the un-rounded fp32 operands.  Bounds 1e-4 max-normalised: two orders of
+    magnitude below the bf16 operand noise floor, so an indexing / epilogue error of any size cannot hide."""
+    import ctypes
+    import torch
+    import torch.nn.functional as F
+    from vista_slam_b200._lib import EPI_BF16, EPI_F32, EPI_GELU, EPI_PIXSHUF, EPI_ROPE, check, cur_stream, lib, ptr
+    torch.manual_seed(7)
+    dev = "cuda"
+    TOL = 1e-4
+    # small-problem route (128-wide single-CTA tiles, TMA epilogue) / 256-wide CTA pairs (TMA epilogue) / N % 256 != 0
+    # (128-wide tiles, staging epilogue)
+    for (M, N, K) in [(777, 512, 256), (4096, 768, 768), (300, 384, 192)]:
+        A = torch.randn(M, K, device=dev)
+        W = torch.randn(N, K, device=dev) / math.sqrt(K)
+        bias = torch.randn(N, device=dev)
+        base = (A.double() @ W.double().t() + bias.double())
+        A3, W3 = split_act(A), split_w(W)
+        for epi, nm, fn in ((EPI_BF16, "bf16", lambda t: t), (EPI_GELU, "gelu", lambda t: F.gelu(t))):
+            if epi == EPI_GELU and N % 256 != 0:
+                continue  # the model has no GELU layer with N % 256 != 0 (no such kernel instance)
+            out = torch.full((M, 3 * N), float("nan"), device=dev, dtype=torch.bfloat16)
+            run_gemm(gemm_desc(epi=epi, A=A3, lda=3 * K, W=W3, ldw=3 * K, M=M, N=N, K=3 * K, bias=bias, out=out, ldo=3 * N,
+                               split_precision=1))
+            torch.cuda.synchronize()
+            report("x3 gemm %s M%d N%d K%d" % (nm, M, N, K), merge3(out, N, nm), fn(base).float(), TOL)
+        # fp32 output accumulating in place (residual stream)
+        x = torch.randn(M, N, device=dev)
+        x0 = x.clone()
+        run_gemm(gemm_desc(epi=EPI_F32, A=A3, lda=3 * K, W=W3, ldw=3 * K, M=M, N=N, K=3 * K, bias=bias, out=x, ldo=N, resid=x,
+                           split_precision=1))
+        torch.cuda.synchronize()
+        report("x3 gemm f32 resid in place M%d N%d K%d" % (M, N, K), x, (x0.double() + base).float(), TOL)
+    # skip tensors + relu copy (staging epilogue), RoPE
+    M, N, K = 500, 256, 256
+    A = torch.randn(M, K, device=dev)
+    W = torch.randn(N, K, device=dev) / math.sqrt(K)
+    bias = torch.randn(N, device=dev)
+    r1, r2 = torch.randn(M, N, device=dev), torch.randn(M, N, device=dev)
+    out = torch.zeros(M, 3 * N, device=dev, dtype=torch.bfloat16)
+    out2 = torch.zeros_like(out)
+    run_gemm(gemm_desc(epi=EPI_BF16, A=split_act(A), lda=3 * K, W=split_w(W), ldw=3 * K, M=M, N=N, K=3 * K, bias=bias, out=out,
+                       ldo=3 * N, out2=out2, resid=split_act(r1), resid2=split_act(r2), split_precision=1))
+    torch.cuda.synchronize()
+    # the skip tensors themselves carry 2^-17 relative representation error
+    ref = (A.double() @ W.double().t() + bias.double() + r1.double() + r2.double()).float()
+    report("x3 gemm bf16 resid x2", merge3(out, N, "resid"), ref, TOL)
+    report("x3 gemm bf16 relu copy", merge3(out2, N, "relu"), ref.relu(), TOL)
+    heads = 4
+    N = heads * 64 * 3
+    W = torch.randn(N, K, device=dev) / math.sqrt(K)
+    bias = torch.randn(N, device=dev)
+    pos = torch.stack([torch.randint(-1, 40, (M,), device=dev), torch.randint(-1, 70, (M,), device=dev)], 1).int().contiguous()
+    out = torch.zeros(M, 3 * N, device=dev, dtype=torch.bfloat16)
+    run_gemm(gemm_desc(epi=EPI_ROPE, A=split_act(A), lda=3 * K, W=split_w(W), ldw=3 * K, M=M, N=N, K=3 * K, bias=bias, out=out,
+                       ldo=3 * N, pos=pos, rope_cols=2 * heads * 64, split_precision=1))
+    torch.cuda.synchronize()
+    base = (A.double() @ W.double().t() + bias.double()).float()
+    ref = base.clone()
+    ref[:, :2 * heads * 64] = rope_ref(base[:, :2 * heads * 64].reshape(M, 2 * heads, 64), pos).reshape(M, -1)
+    report("x3 gemm rope", merge3(out, N, "rope"), ref, TOL)
+    # implicit-GEMM conv with a skip tensor
+    nimg, H, Wd, Cin, Cout = 2, 14, 18, 128, 256
+    x = torch.randn(nimg, H, Wd, Cin, device=dev)
+    wt = torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(9 * Cin)
+    b = torch.randn(Cout, device=dev)
+    wp3 = torch.cat([split_w(wt[:, :, kh, kw]).view(Cout, 1, 3 * Cin) for kh in range(3) for kw in range(3)], 1)
+    wp3 = wp3.reshape(Cout, 27 * Cin).contiguous()
+    r1 = torch.randn(nimg, H, Wd, Cout, device=dev)
+    out = torch.zeros(nimg, H, Wd, 3 * Cout, device=dev, dtype=torch.bfloat16)
+    run_gemm(gemm_desc(conv3x3=1, epi=EPI_BF16, A=split_act(x), W=wp3, ldw=27 * Cin, N=Cout, K=27 * Cin, nimg=nimg, H=H, Wd=Wd,
+                       Cin=3 * Cin, bias=b, out=out, ldo=3 * Cout, resid=split_act(r1), split_precision=1))
+    torch.cuda.synchronize()
+    ref = (F.conv2d(x.double().permute(0, 3, 1, 2), wt.double(), b.double(), padding=1).permute(0, 2, 3, 1) + r1.double()).float()
+    report("x3 conv3x3 + skip", merge3(out, Cout, "conv"), ref, TOL)
+    # ConvTranspose (k = stride = 2) as GEMM + pixel shuffle
+    hh, ww, C = 6, 10, 192
+    T = 2 * hh * ww
+    a = torch.randn(T, C, device=dev)
+    wT = torch.randn(C, C, 2, 2, device=dev) / math.sqrt(C)  # [Cin][Cout][k][k]
+    bT = torch.randn(C, device=dev)
+    wg = wT.permute(2, 3, 1, 0).reshape(4 * C, C).contiguous()  # [(kh,kw,co)][ci]
+    out = torch.zeros(2, 2 * hh, 2 * ww, 3 * C, device=dev, dtype=torch.bfloat16)
+    run_gemm(gemm_desc(epi=EPI_PIXSHUF, A=split_act(a), lda=3 * C, W=split_w(wg), ldw=3 * C, M=T, N=4 * C, K=3 * C, bias=bT,
+                       out=out, ps_k=2, ps_cout=C, ps_h=hh, ps_w=ww, split_precision=1))
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(a.double().view(2, hh, ww, C).permute(0, 3, 1, 2), wT.double(), bT.double(), stride=2)
+    report("x3 convT pixel-shuffle", merge3(out, C, "convT"), ref.permute(0, 2, 3, 1).float(), TOL)
 
 
 def group_perf():

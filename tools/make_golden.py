@@ -27,7 +27,13 @@ CASES = [
     # name, B, H, W, weight seed, image seed
     ("pair_64x80", 1, 64, 80, 0, 1234),     # odd token-grid width (5): exercises the refinenet4 crop
     ("pair_b2_48x64", 2, 48, 64, 0, 77),    # batch 2, 3x4 token grid
+    ("pair_224x224", 1, 224, 224, 0, 1234),  # cfg-1: the reference's native size (sta_model.py:34)
+    ("pair_384x512", 1, 384, 512, 0, 1234),  # one cfg-2 pair (H = 384, W = 512); bf16-representable images
 ]
+# cases whose images are rounded to bf16 first (cfg-2 feeds bf16 images; the reference consumes them upcast to fp32)
+BF16_IMAGES = {"pair_384x512"}
+# the large case stores only what the GPU tests compare (outputs + one feature per stage) to keep the fixture small
+SLIM = {"pair_384x512"}
 
 
 def maxrel(a, b):
@@ -35,6 +41,7 @@ def maxrel(a, b):
 
 
 def main():
+    only = set(sys.argv[1:])  # optional: regenerate only the named cases
     torch.set_num_threads(usable_cpus())
     STA = import_reference_sta()
     t0 = time.time()
@@ -48,7 +55,11 @@ def main():
     outdir = os.path.join(ROOT, "tests", "golden")
     for name, B, H, W, wseed, iseed in CASES:
         assert wseed == 0
+        if only and name not in only:
+            continue
         img1, img2 = make_images(B, H, W, iseed)
+        if name in BF16_IMAGES:
+            img1, img2 = img1.bfloat16().float(), img2.bfloat16().float()
         ts = torch.tensor([[H, W]] * B)
         views = {"main_view": {"img": img1, "true_shape": ts},
                  "neighbor_views": [{"img": img2, "true_shape": ts}], "loop_views": []}
@@ -74,8 +85,11 @@ def main():
             "enc_feat1": f1, "dec1_6": d1[6], "dec1_9": d1[9], "dec1_12": d1[12], "dec2_12": d2[12],
             "pos1": pos1,
         }
+        if name in SLIM:
+            for k in ("dec1_6", "dec1_9", "dec2_12", "pos1"):
+                arrays.pop(k)
         meta = {"case": name, "B": B, "H": H, "W": W, "weight_seed": wseed, "image_seed": iseed,
-                "torch": torch.__version__, "reference_commit": "b13ac44", "precision": "fp32 CPU",
+                "bf16_images": name in BF16_IMAGES, "torch": torch.__version__, "reference_commit": "b13ac44", "precision": "fp32 CPU",
                 "oracle_vs_reference_maxrel": dev}
         np.savez_compressed(os.path.join(outdir, name + ".npz"), meta=json.dumps(meta),
                             **{k: v.detach().cpu().numpy() for k, v in arrays.items()})

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("STA_B200_LIB") or os.path.join(_HERE, "csrc", "libsta_b200.so")  # env override: A/B timing of builds
 
 EPI_BF16, EPI_GELU, EPI_F32, EPI_ROPE, EPI_PIXSHUF, EPI_HEAD = range(6)
+PRECISION_BF16, PRECISION_X3 = 0, 1
 
 
 class StaGemmDesc(Structure):
@@ -29,6 +30,7 @@ class StaGemmDesc(Structure):
         ("ps_k", c_int), ("ps_cout", c_int), ("ps_h", c_int), ("ps_w", c_int),
         ("head_w", c_void_p), ("head_b", c_void_p), ("pts3d", c_void_p), ("conf", c_void_p),
         ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_int64),
+        ("split_precision", c_int),
     ]
 
 
@@ -51,6 +53,7 @@ def lib():
     L.sta_version.restype = i
     L.sta_device_synchronize.restype = i
     L.sta_create.argtypes = [POINTER(vp)]
+    L.sta_create_ex.argtypes = [POINTER(vp), i]
     L.sta_destroy.argtypes = [vp]
     L.sta_destroy.restype = None
     L.sta_load_tensor.argtypes = [vp, c_char_p, vp, POINTER(c_int64), i, i]

@@ -558,6 +558,118 @@ attention_row0_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, int q_
   }
 }
 
+// ---------------------------------------------------------------------------
+// Split-precision parity mode (common.cuh): exact-softmax attention in fp32 on the CUDA cores.  Q, K, V rows are
+// (hi | lo | hi) bf16; every value is reconstructed as hi + lo (16-17 significant bits), scores, the online softmax
+// (full-precision exp2f) and P V are fp32, the output is stored as (hi | lo | hi).  One thread per query row (its q
+// and output accumulator live in registers), 32-key tiles of K and V staged in shared memory as fp32.  Not a
+// performance path: it exists so that the whole model can be checked against the fp32 reference below the bf16
+// noise floor (tests, tools/parity_report.py).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+attention_x3_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, int q_col0, const __nv_bfloat16* __restrict__ k,
+                    long long ldk, int k_col0, const __nv_bfloat16* __restrict__ v, long long ldv, int v_col0,
+                    __nv_bfloat16* __restrict__ out, long long ldo, int nq, int nk, int batch, int kv_batch_shift,
+                    float scale_log2) {
+  __shared__ __align__(16) float Ks[32][64];
+  __shared__ __align__(16) float Vs[32][64];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int kvb = (b + kv_batch_shift) % batch;
+  const int tid = threadIdx.x;
+  const int row = blockIdx.x * 128 + tid;
+  const bool valid = row < nq;
+  float qv[64], o[64];
+  {
+    const __nv_bfloat16* qp = q + (static_cast<long long>(b) * nq + (valid ? row : 0)) * ldq + q_col0 + head * 64;
+    const long long lo_off = ldq / 3;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) {
+      qv[d] = valid ? (__bfloat162float(qp[d]) + __bfloat162float(qp[lo_off + d])) * scale_log2 : 0.f;
+      o[d] = 0.f;
+    }
+  }
+  float m = -INFINITY, l = 0.f;
+  const __nv_bfloat16* kb = k + static_cast<long long>(kvb) * nk * ldk + k_col0 + head * 64;
+  const __nv_bfloat16* vb = v + static_cast<long long>(kvb) * nk * ldv + v_col0 + head * 64;
+  const long long klo = ldk / 3, vlo = ldv / 3;
+  for (int j0 = 0; j0 < nk; j0 += 32) {
+    __syncthreads();
+    {  // stage 32 keys x 64 dims of K and V as fp32: thread -> (key = tid / 4, 16 dims)
+      const int key = tid >> 2, d0 = (tid & 3) * 16;
+      const int j = j0 + key;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        float kf = 0.f, vf = 0.f;
+        if (j < nk) {
+          const __nv_bfloat16* kr = kb + static_cast<long long>(j) * ldk + d0 + d;
+          const __nv_bfloat16* vr = vb + static_cast<long long>(j) * ldv + d0 + d;
+          kf = __bfloat162float(kr[0]) + __bfloat162float(kr[klo]);
+          vf = __bfloat162float(vr[0]) + __bfloat162float(vr[vlo]);
+        }
+        Ks[key][d0 + d] = kf;
+        Vs[key][d0 + d] = vf;
+      }
+    }
+    __syncthreads();
+    const int nv = (nk - j0 < 32) ? (nk - j0) : 32;
+    float sc[32];
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 64; d += 4) {
+        const float4 kk = *reinterpret_cast<const float4*>(&Ks[jj][d]);
+        a0 = fmaf(qv[d], kk.x, a0);
+        a1 = fmaf(qv[d + 1], kk.y, a1);
+        a2 = fmaf(qv[d + 2], kk.z, a2);
+        a3 = fmaf(qv[d + 3], kk.w, a3);
+      }
+      const float sv = (jj < nv) ? (a0 + a1) + (a2 + a3) : -INFINITY;
+      sc[jj] = sv;
+      tmax = fmaxf(tmax, sv);
+    }
+    const float m_new = fmaxf(m, tmax);  // finite: every tile holds at least one valid key
+    const float corr = exp2f(m - m_new);  // first tile: exp2f(-inf) = 0
+    l *= corr;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) o[d] *= corr;
+    m = m_new;
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      const float pj = exp2f(sc[jj] - m);  // masked keys: exp2f(-inf) = 0
+      l += pj;
+#pragma unroll
+      for (int d = 0; d < 64; d += 4) {
+        const float4 vv = *reinterpret_cast<const float4*>(&Vs[jj][d]);
+        o[d] = fmaf(pj, vv.x, o[d]);
+        o[d + 1] = fmaf(pj, vv.y, o[d + 1]);
+        o[d + 2] = fmaf(pj, vv.z, o[d + 2]);
+        o[d + 3] = fmaf(pj, vv.w, o[d + 3]);
+      }
+    }
+  }
+  if (valid) {
+    const float inv_l = 1.0f / l;
+    __nv_bfloat16* op = out + (static_cast<long long>(b) * nq + row) * ldo + head * 64;
+    const long long w = ldo / 3;
+#pragma unroll
+    for (int d = 0; d < 64; d += 8) {
+      float r[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = o[d + i] * inv_l;
+      const uint4 hi = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                                  pack_bf16x2(r[6], r[7]));
+      *reinterpret_cast<uint4*>(op + d) = hi;
+      *reinterpret_cast<uint4*>(op + w + d) = make_uint4(pack_bf16x2_resid(r[0], r[1]), pack_bf16x2_resid(r[2], r[3]),
+                                                         pack_bf16x2_resid(r[4], r[5]), pack_bf16x2_resid(r[6], r[7]));
+      *reinterpret_cast<uint4*>(op + 2 * w + d) = hi;
+    }
+  }
+}
+
 int make_qkv_map(CUtensorMap* m, const bf16* base, long long ld, int ntok, int batch) {
   uint64_t dims[3] = {(uint64_t)ld, (uint64_t)ntok, (uint64_t)batch};
   uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)ntok};
@@ -571,12 +683,19 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   STA_REQUIRE(a.batch > 0 && a.heads > 0 && a.nq > 0 && a.nk > 0, "empty attention problem");
   STA_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "row strides must be 16B multiples");
   STA_REQUIRE(a.q_col0 % 8 == 0 && a.k_col0 % 8 == 0 && a.v_col0 % 8 == 0, "column offsets must be 16B multiples");
-  static bool attr_set = false;
-  if (!attr_set) {
-    STA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)ATT_SMEM));
-    attr_set = true;
+  if (a.split) {
+    STA_REQUIRE(a.ldq % 3 == 0 && a.ldk % 3 == 0 && a.ldv % 3 == 0 && a.ldo % 3 == 0 && (a.ldo / 3) % 8 == 0,
+                "split-precision rows are (hi | lo | hi): strides must be 3 x the logical width");
+    STA_REQUIRE(a.heads <= 65535 && a.batch <= 65535, "grid limits");
+    STA_CHECK_CUDA(launch_pdl(attention_x3_kernel, dim3((a.nq + 127) / 128, a.heads, a.batch), dim3(128), 0, stream, 1, a.q,
+                              a.ldq, a.q_col0, a.k, a.ldk, a.k_col0, a.v, a.ldv, a.v_col0, a.out, a.ldo, a.nq, a.nk, a.batch,
+                              a.kv_batch_shift, a.scale * 1.4426950408889634f));
+    return 0;
   }
+  static PerDeviceOnce once;  // the opt-in is per device, not per process
+  STA_CHECK_CUDA(once.run([&] {
+    return cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
+  }));
   CUtensorMap tmQ, tmK, tmV;
   if (make_qkv_map(&tmQ, a.q, a.ldq, a.nq, a.batch)) return 1;
   if (make_qkv_map(&tmK, a.k, a.ldk, a.nk, a.batch)) return 1;

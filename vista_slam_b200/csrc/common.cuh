@@ -331,6 +331,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+// Split-precision ("x3") parity mode: a value v travels as two bf16 numbers hi = bf16(v), lo = bf16(v - hi)
+// (16-17 significant bits together).  A logical [rows][C] activation is stored as [rows][3C] = (hi | lo | hi) and a
+// weight [N][K] as [N][3K] = (hi | hi | lo), so that the UNCHANGED bf16 tensor-core mainloop over K' = 3K computes
+// a_hi w_hi + a_lo w_hi + a_hi w_lo with fp32 accumulation (the dropped a_lo w_lo term is 2^-18 relative).
+__device__ __forceinline__ float bf16_resid(float v) { return v - __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ uint32_t pack_bf16x2_resid(float lo, float hi) {
+  return pack_bf16x2(bf16_resid(lo), bf16_resid(hi));
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

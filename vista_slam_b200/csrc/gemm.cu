@@ -38,11 +38,9 @@ static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        int num_tiles, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG, EW, EPI, TMA>;
   auto kern = gemm_tc_kernel<BN, AMODE, EPI, CG, EW, TMA>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    STA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce once;  // the opt-in is per device, not per process
+  STA_CHECK_CUDA(once.run(
+      [&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES); }));
   // persistent: one CTA (CG=1) or one CTA pair (CG=2) per work-item slot
   const int max_items = num_sms() / CG;
   const int items = num_tiles < max_items ? num_tiles : max_items;
@@ -68,6 +66,8 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
     p.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
   }
   STA_REQUIRE(p.N % 32 == 0, "N must be a multiple of 32");
+  STA_REQUIRE(!p.split || g.epi == EPI_F32 || g.epi == EPI_HEAD || g.epi == EPI_PIXSHUF || p.ldo >= 3LL * p.N,
+              "split-precision bf16 outputs need ldo >= 3N");
   STA_REQUIRE(g.A != nullptr && g.Wt != nullptr, "null operand");
   STA_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.Wt) & 15) == 0,
               "operands must be 16-byte aligned");
@@ -175,7 +175,8 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
     if (make_tmap(&tmC, g.splitk_ws, 1, 2, dims, strides, box)) return 1;
   } else if (tma) {
     ksplit = 1;
-    uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M};
+    // split-precision mode: bf16 rows are (hi | lo | hi), 3N wide
+    uint64_t dims[2] = {(uint64_t)p.N * ((p.split && esz == 2) ? 3 : 1), (uint64_t)p.M};
     uint64_t strides[1] = {(uint64_t)p.ldo * esz};
     uint32_t box[2] = {(uint32_t)(128 / esz), 32};
     if (make_tmap(&tmC, p.out, esz == 4, 2, dims, strides, box)) return 1;

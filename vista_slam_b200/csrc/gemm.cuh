@@ -60,6 +60,10 @@ struct GemmParams {
   int ksplit;      // >= 1
   int split_rows;  // rows of one partial slice (multiple of 128)
   int c_reduce;         // TMA epilogue, EPI_F32: out += result (in-place fp32 residual stream) via bulk reduce-add
+  // split-precision parity mode (common.cuh): the operands are already (hi | lo | hi) x (hi | hi | lo) expanded along K
+  // (K here is the physical 3K); bf16 outputs / bf16 skip tensors use the (hi | lo | hi) row layout with logical
+  // width N (ldo = 3N).  fp32 outputs are unaffected.
+  int split;
   long long* dbg;       // optional clock64 trace (env STA_GEMM_TRACE), else null
 };
 
@@ -145,6 +149,15 @@ __device__ __forceinline__ uint2 pack4_bf16(const float4& v) {
 }
 __device__ __forceinline__ void add_bf16x4(float4& v, uint2 q) {
   v.x += bf16_lo(q.x); v.y += bf16_hi(q.x); v.z += bf16_lo(q.y); v.w += bf16_hi(q.y);
+}
+// bf16 store of 4 values at p; in split mode also the residual part at p + w and the second hi copy at p + 2w
+__device__ __forceinline__ void store4_bf16(__nv_bfloat16* p, const float4& v, int split, long long w) {
+  const uint2 hi = pack4_bf16(v);
+  *reinterpret_cast<uint2*>(p) = hi;
+  if (split) {
+    *reinterpret_cast<uint2*>(p + w) = make_uint2(pack_bf16x2_resid(v.x, v.y), pack_bf16x2_resid(v.z, v.w));
+    *reinterpret_cast<uint2*>(p + 2 * w) = hi;
+  }
 }
 
 template <int BN, int AMODE, int EPI, int EW>
@@ -354,21 +367,30 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
             if (p.resid) { v.x += rf[k].x; v.y += rf[k].y; v.z += rf[k].z; v.w += rf[k].w; }
             if (ok) *reinterpret_cast<float4*>(op) = v;
           } else if constexpr (EPI == EPI_PIXSHUF) {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (orow_c[it] + pix_off) * p.ps_cout + co + cc;
-            if (ok) *reinterpret_cast<uint2*>(op) = pack4_bf16(v);
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                (orow_c[it] + pix_off) * (p.split ? 3 * p.ps_cout : p.ps_cout) + co + cc;
+            if (ok) store4_bf16(op, v, p.split, p.ps_cout);
           } else {
             const long long off = orow_c[it] * p.ldo + col + cc;
             if constexpr (EPI == EPI_BF16) {
-              if (p.resid) add_bf16x4(v, ra[k]);
-              if (p.resid2) add_bf16x4(v, rb[k]);
+              if (p.resid) {
+                add_bf16x4(v, ra[k]);
+                if (p.split && ok)  // residual (lo) part of the skip tensor
+                  add_bf16x4(v, *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + off + p.N));
+              }
+              if (p.resid2) {
+                add_bf16x4(v, rb[k]);
+                if (p.split && ok)
+                  add_bf16x4(v, *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.resid2) + off + p.N));
+              }
               if (p.relu_main) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             }
             if constexpr (EPI == EPI_GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-            if (p.out && ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = pack4_bf16(v);
+            if (p.out && ok) store4_bf16(reinterpret_cast<__nv_bfloat16*>(p.out) + off, v, p.split, p.N);
             if constexpr (EPI == EPI_BF16) {
               if (p.out2 && ok) {
                 v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + off) = pack4_bf16(v);
+                store4_bf16(reinterpret_cast<__nv_bfloat16*>(p.out2) + off, v, p.split, p.N);
               }
             }
           }
@@ -458,17 +480,25 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     }
   }
 
+  // Split-precision parity mode, bf16 outputs: the tile is drained twice -- pass 0 stores hi = bf16(v) at columns
+  // [col, ..) and [2N + col, ..), pass 1 recomputes v from TMEM and stores lo = bf16(v - hi) at [N + col, ..) -- so the
+  // production register footprint is unchanged.  The accumulator stage is released in the last pass only.
+  const int npass = (!OUT_F32 && p.split) ? 2 : 1;
+  const bool has_bias = p.bias != nullptr;
+#pragma unroll 1
+  for (int pass = 0; pass < npass; ++pass) {
   // bias of chunk c is loaded one chunk ahead (warp-uniform addresses: L1 broadcast), so its latency never sits
   // between the TMEM load and the math
   float4 bcur[8];
-  const bool has_bias = p.bias != nullptr;
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     bcur[j] = has_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + colbase) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
 
-  mbar_wait(tfull_bar, tfull_phase);
-  tc_fence_after();
-  if (trace) trace[0] = clock64();
+  if (pass == 0) {
+    mbar_wait(tfull_bar, tfull_phase);
+    tc_fence_after();
+    if (trace) trace[0] = clock64();
+  }
   uint32_t acc[PF ? 2 : 1][32];
   tmem_ld32(taddr, acc[0]);
 #pragma unroll
@@ -486,7 +516,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
 #pragma unroll
         for (int j = 0; j < 8; ++j) bcur[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col + 32) + j);
       }
-    } else {
+    } else if (pass == npass - 1) {
       release();
     }
     if (trace) trace[1 + 3 * c] = clock64();
@@ -544,6 +574,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
       }
+      if (pass == 1) {  // residual part: lo = v - bf16(v)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = bf16_resid(v[i]);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((sub * 4 + j) ^ sx) << 4)),
@@ -554,7 +588,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(tmC, cbuf, col - 32, srow0);
+          tma_store_2d(tmC, cbuf, col - 32 + pass * p.N, srow0);
+          if (p.split && pass == 0) tma_store_2d(tmC, cbuf, col - 32 + 2 * p.N, srow0);  // second hi copy
           tma_store_commit();
         }
       }
@@ -564,6 +599,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     }
     if (trace) trace[3 + 3 * c] = clock64();
   }
+  }  // pass
 }
 
 template <int BN, int AMODE, int EPI, int CG, int EW, bool TMA>
@@ -644,7 +680,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
   tc_fence_before();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  __syncthreads();  // CTA-level barrier also for CG == 2: orders the barrier init / TMEM-slot write for this CTA's readers
+                    // (and is what compute-sanitizer racecheck models; barrier.cluster alone is reported as a hazard)
+  if constexpr (CG == 2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();               // previous kernel's outputs (A operand, residuals) are complete and visible

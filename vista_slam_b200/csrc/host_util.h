@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
+#include <mutex>
 #include <string>
 
 namespace sta {
@@ -47,7 +49,28 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 int make_tmap(CUtensorMap* out, const void* base, int is_f32, int rank, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box);
 
-int num_sms();
+int num_sms();  // of the CURRENT device (cached per device)
+
+// One-time per-DEVICE setup at a call site (cudaFuncSetAttribute is per device/context, not per process):
+//   static PerDeviceOnce once;  STA_CHECK_CUDA(once.run([&] { return cudaFuncSetAttribute(...); }));
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  std::mutex mu;
+  template <typename F>
+  cudaError_t run(F&& f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return f();  // beyond the bitmap: just repeat the (idempotent) setup
+    const unsigned long long bit = 1ull << dev;
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.load(std::memory_order_relaxed) & bit) return cudaSuccess;
+    e = f();
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+  }
+};
 
 // Launch with programmatic stream serialization (PDL) and an optional cluster size.  The kernel MUST call
 // sta::pdl_wait() before its first global-memory access.

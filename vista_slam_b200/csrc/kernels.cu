@@ -25,10 +25,11 @@ template <int C>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int rows, float eps, const float* __restrict__ g1,
                  const float* __restrict__ b1, __nv_bfloat16* __restrict__ out1, const float* __restrict__ g2,
-                 const float* __restrict__ b2, __nv_bfloat16* __restrict__ out2, int drop_first_of) {
+                 const float* __restrict__ b2, __nv_bfloat16* __restrict__ out2, int drop_first_of, int split) {
   pdl_wait();
   pdl_launch_dependents();
   constexpr int V = C / 128;  // float4 per lane
+  const long long ldo = split ? 3 * C : C;  // split-precision mode: rows are (hi | lo | hi)
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -67,32 +68,42 @@ layernorm_kernel(const float* __restrict__ x, int rows, float eps, const float* 
     {
       const float4 g = __ldg(reinterpret_cast<const float4*>(g1) + c4);
       const float4 bb = __ldg(reinterpret_cast<const float4*>(b1) + c4);
+      const float y0 = n0 * g.x + bb.x, y1 = n1 * g.y + bb.y, y2 = n2 * g.z + bb.z, y3 = n3 * g.w + bb.w;
       uint2 q;
-      q.x = pack_bf16x2(n0 * g.x + bb.x, n1 * g.y + bb.y);
-      q.y = pack_bf16x2(n2 * g.z + bb.z, n3 * g.w + bb.w);
-      reinterpret_cast<uint2*>(out1 + orow * C)[c4] = q;
+      q.x = pack_bf16x2(y0, y1);
+      q.y = pack_bf16x2(y2, y3);
+      reinterpret_cast<uint2*>(out1 + orow * ldo)[c4] = q;
+      if (split) {
+        reinterpret_cast<uint2*>(out1 + orow * ldo + C)[c4] = make_uint2(pack_bf16x2_resid(y0, y1), pack_bf16x2_resid(y2, y3));
+        reinterpret_cast<uint2*>(out1 + orow * ldo + 2 * C)[c4] = q;
+      }
     }
     if (out2) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(g2) + c4);
       const float4 bb = __ldg(reinterpret_cast<const float4*>(b2) + c4);
+      const float y0 = n0 * g.x + bb.x, y1 = n1 * g.y + bb.y, y2 = n2 * g.z + bb.z, y3 = n3 * g.w + bb.w;
       uint2 q;
-      q.x = pack_bf16x2(n0 * g.x + bb.x, n1 * g.y + bb.y);
-      q.y = pack_bf16x2(n2 * g.z + bb.z, n3 * g.w + bb.w);
-      reinterpret_cast<uint2*>(out2 + orow * C)[c4] = q;
+      q.x = pack_bf16x2(y0, y1);
+      q.y = pack_bf16x2(y2, y3);
+      reinterpret_cast<uint2*>(out2 + orow * ldo)[c4] = q;
+      if (split) {
+        reinterpret_cast<uint2*>(out2 + orow * ldo + C)[c4] = make_uint2(pack_bf16x2_resid(y0, y1), pack_bf16x2_resid(y2, y3));
+        reinterpret_cast<uint2*>(out2 + orow * ldo + 2 * C)[c4] = q;
+      }
     }
   }
 }
 
 int launch_layernorm(const float* x, int rows, int C, float eps, const float* g1, const float* b1, bf16* out1,
-                     const float* g2, const float* b2, bf16* out2, int drop_first_of, cudaStream_t stream) {
+                     const float* g2, const float* b2, bf16* out2, int drop_first_of, cudaStream_t stream, int split) {
   if (rows <= 0) return 0;
   const int grid = (rows + 7) / 8;
   if (C == 1024)
     STA_CHECK_CUDA(launch_pdl(layernorm_kernel<1024>, dim3(grid), dim3(256), 0, stream, 1, x, rows, eps, g1, b1, out1, g2, b2, out2,
-                              drop_first_of));
+                              drop_first_of, split));
   else if (C == 768)
     STA_CHECK_CUDA(launch_pdl(layernorm_kernel<768>, dim3(grid), dim3(256), 0, stream, 1, x, rows, eps, g1, b1, out1, g2, b2, out2,
-                              drop_first_of));
+                              drop_first_of, split));
   else {
     set_last_error("layernorm: C must be 768 or 1024");
     return 2;
@@ -108,7 +119,7 @@ int launch_layernorm(const float* x, int rows, int C, float eps, const float* g1
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-patch_im2col_kernel(const T* __restrict__ img, int B, int H, int W, __nv_bfloat16* __restrict__ out) {
+patch_im2col_kernel(const T* __restrict__ img, int B, int H, int W, __nv_bfloat16* __restrict__ out, int split) {
   pdl_wait();
   pdl_launch_dependents();
   const int h = H / 16, w = W / 16;
@@ -132,19 +143,27 @@ patch_im2col_kernel(const T* __restrict__ img, int B, int H, int W, __nv_bfloat1
   q.y = pack_bf16x2(f[2], f[3]);
   q.z = pack_bf16x2(f[4], f[5]);
   q.w = pack_bf16x2(f[6], f[7]);
-  reinterpret_cast<uint4*>(out)[idx] = q;
+  if (!split) {
+    reinterpret_cast<uint4*>(out)[idx] = q;
+  } else {  // rows of 3 x 768: (hi | lo | hi)
+    uint4* orow = reinterpret_cast<uint4*>(out) + patch * (3 * 96) + chunk;
+    orow[0] = q;
+    orow[96] = make_uint4(pack_bf16x2_resid(f[0], f[1]), pack_bf16x2_resid(f[2], f[3]), pack_bf16x2_resid(f[4], f[5]),
+                          pack_bf16x2_resid(f[6], f[7]));
+    orow[192] = q;
+  }
 }
 
-int launch_patch_im2col(const void* img, int img_is_bf16, int B, int H, int W, bf16* out, cudaStream_t stream) {
+int launch_patch_im2col(const void* img, int img_is_bf16, int B, int H, int W, bf16* out, cudaStream_t stream, int split) {
   STA_REQUIRE(H % 16 == 0 && W % 16 == 0, "image height and width must be multiples of the patch size 16");
   const long long total = static_cast<long long>(B) * (H / 16) * (W / 16) * 96;
   const int grid = static_cast<int>((total + 255) / 256);
   if (img_is_bf16)
     STA_CHECK_CUDA(launch_pdl(patch_im2col_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, 1,
-                              static_cast<const __nv_bfloat16*>(img), B, H, W, out));
+                              static_cast<const __nv_bfloat16*>(img), B, H, W, out, split));
   else
     STA_CHECK_CUDA(launch_pdl(patch_im2col_kernel<float>, dim3(grid), dim3(256), 0, stream, 1, static_cast<const float*>(img), B, H, W,
-                              out));
+                              out, split));
   STA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -195,7 +214,7 @@ int launch_pos_from_int64(const long long* pos64, int rows, int* pos32, cudaStre
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long rows, int C,
-                     int drop_first_of) {
+                     int drop_first_of, int split) {
   pdl_wait();
   pdl_launch_dependents();
   const int cpr = C / 8;
@@ -217,14 +236,23 @@ cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ o
   q.y = pack_bf16x2(a.z, a.w);
   q.z = pack_bf16x2(b.x, b.y);
   q.w = pack_bf16x2(b.z, b.w);
-  *reinterpret_cast<uint4*>(out + orow * C + ch * 8) = q;
+  if (!split) {
+    *reinterpret_cast<uint4*>(out + orow * C + ch * 8) = q;
+  } else {
+    __nv_bfloat16* o = out + orow * 3 * C + ch * 8;
+    *reinterpret_cast<uint4*>(o) = q;
+    *reinterpret_cast<uint4*>(o + C) = make_uint4(pack_bf16x2_resid(a.x, a.y), pack_bf16x2_resid(a.z, a.w),
+                                                  pack_bf16x2_resid(b.x, b.y), pack_bf16x2_resid(b.z, b.w));
+    *reinterpret_cast<uint4*>(o + 2 * C) = q;
+  }
 }
-int launch_cast_f32_bf16(const float* in, bf16* out, long long rows, int C, int drop_first_of, cudaStream_t stream) {
+int launch_cast_f32_bf16(const float* in, bf16* out, long long rows, int C, int drop_first_of, cudaStream_t stream,
+                         int split) {
   STA_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
   const long long total = rows * (C / 8);
   if (total == 0) return 0;
   STA_CHECK_CUDA(launch_pdl(cast_f32_bf16_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, stream, 1, in, out, rows,
-                            C, drop_first_of));
+                            C, drop_first_of, split));
   STA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -275,7 +303,7 @@ int launch_copy_f32(const float* in, float* out, long long n, cudaStream_t strea
 constexpr int kUpsPix = 4;
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int nimg, int H, int W, int C,
-                  int OH, int OW) {
+                  int OH, int OW, int split) {
   pdl_wait();
   pdl_launch_dependents();
   // the interpolation grid is always the full 2H x 2W one; (OH, OW) <= (2H, 2W) only crops the output
@@ -292,10 +320,39 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restric
   const int y0 = static_cast<int>(fy);
   const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
   const float ly = fy - y0, hy = 1.f - ly;
-  const __nv_bfloat16* row0 = in + (static_cast<long long>(n) * H + y0) * W * C + ch * 8;
-  const __nv_bfloat16* row1 = in + (static_cast<long long>(n) * H + y1) * W * C + ch * 8;
-  __nv_bfloat16* orow = out + (static_cast<long long>(n) * OH + oy) * OW * C + ch * 8;
+  const int PC = split ? 3 * C : C;  // physical channels per pixel (split-precision mode: hi | lo | hi)
+  const __nv_bfloat16* row0 = in + (static_cast<long long>(n) * H + y0) * W * PC + ch * 8;
+  const __nv_bfloat16* row1 = in + (static_cast<long long>(n) * H + y1) * W * PC + ch * 8;
+  __nv_bfloat16* orow = out + (static_cast<long long>(n) * OH + oy) * OW * PC + ch * 8;
   const int ox_base = blockIdx.x * (ppb * kUpsPix) + pl;
+  if (split) {
+    // parity mode (not performance critical): interpolate hi + lo in fp32, store (hi | lo | hi)
+    for (int k = 0; k < kUpsPix; ++k) {
+      const int ox = ox_base + k * ppb;
+      if (ox >= OW) break;
+      const float fx = sx * ox;
+      int x0 = static_cast<int>(fx);
+      x0 = x0 < W - 1 ? x0 : W - 1;
+      const int x1 = x0 + (x0 < W - 1 ? 1 : 0);
+      const float lx = fx - x0, hx = 1.f - lx;
+      float r[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        auto val = [&](const __nv_bfloat16* rp, int x) {
+          return __bfloat162float(rp[x * PC + i]) + __bfloat162float(rp[x * PC + C + i]);
+        };
+        r[i] = hy * (hx * val(row0, x0) + lx * val(row0, x1)) + ly * (hx * val(row1, x0) + lx * val(row1, x1));
+      }
+      __nv_bfloat16* o = orow + static_cast<long long>(ox) * PC;
+      const uint4 hi = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                                  pack_bf16x2(r[6], r[7]));
+      *reinterpret_cast<uint4*>(o) = hi;
+      *reinterpret_cast<uint4*>(o + C) = make_uint4(pack_bf16x2_resid(r[0], r[1]), pack_bf16x2_resid(r[2], r[3]),
+                                                    pack_bf16x2_resid(r[4], r[5]), pack_bf16x2_resid(r[6], r[7]));
+      *reinterpret_cast<uint4*>(o + 2 * C) = hi;
+    }
+    return;
+  }
   uint4 q00[kUpsPix], q01[kUpsPix], q10[kUpsPix], q11[kUpsPix];
   float lxs[kUpsPix];
 #pragma unroll
@@ -328,14 +385,15 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restric
     *reinterpret_cast<uint4*>(orow + static_cast<long long>(ox) * C) = make_uint4(r[0], r[1], r[2], r[3]);
   }
 }
-int launch_upsample2x(const bf16* in, bf16* out, int nimg, int H, int W, int C, int OH, int OW, cudaStream_t stream) {
+int launch_upsample2x(const bf16* in, bf16* out, int nimg, int H, int W, int C, int OH, int OW, cudaStream_t stream,
+                      int split) {
   STA_REQUIRE(C % 8 == 0 && C / 8 <= 256, "C must be a multiple of 8, at most 2048");
   STA_REQUIRE(OH <= 2 * H && OW <= 2 * W && OH > 0 && OW > 0, "output crop must fit inside the 2x grid");
   STA_REQUIRE(OH <= 65535 && nimg <= 65535, "grid limits");
   if (nimg == 0) return 0;
   const int ppb = 256 / (C / 8);
   const int gx = (OW + ppb * kUpsPix - 1) / (ppb * kUpsPix);
-  STA_CHECK_CUDA(launch_pdl(upsample2x_kernel, dim3(gx, OH, nimg), dim3(256), 0, stream, 1, in, out, nimg, H, W, C, OH, OW));
+  STA_CHECK_CUDA(launch_pdl(upsample2x_kernel, dim3(gx, OH, nimg), dim3(256), 0, stream, 1, in, out, nimg, H, W, C, OH, OW, split));
   STA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -43,19 +43,24 @@ struct AttnLaunch {
   // handles query rows [1, nq) -- whole 128-row tiles -- and a small SIMT kernel handles query row 0 of every
   // (sample, head), instead of paying a whole extra query tile for one row.
   int split_first_row = 0;
+  // split-precision parity mode (common.cuh): q/k/v/out rows are (hi | lo | hi) with ld* the physical (3x) strides;
+  // an fp32 SIMT kernel with exact exp2f computes softmax(q k^T) v from hi + lo and stores (hi | lo | hi).
+  int split = 0;
 };
 int launch_attention(const AttnLaunch& a, cudaStream_t stream);
 
 // ---- bandwidth-bound kernels (kernels.cu) ----
 int launch_layernorm(const float* x, int rows, int C, float eps, const float* g1, const float* b1, bf16* out1,
-                     const float* g2, const float* b2, bf16* out2, int drop_first_of, cudaStream_t stream);
-int launch_patch_im2col(const void* img, int img_is_bf16, int B, int H, int W, bf16* out, cudaStream_t stream);
+                     const float* g2, const float* b2, bf16* out2, int drop_first_of, cudaStream_t stream, int split = 0);
+int launch_patch_im2col(const void* img, int img_is_bf16, int B, int H, int W, bf16* out, cudaStream_t stream, int split = 0);
 int launch_make_positions(int* pos, int B, int h, int w, int with_pose_token, cudaStream_t stream);
 int launch_pos_from_int64(const long long* pos64, int rows, int* pos32, cudaStream_t stream);
-int launch_cast_f32_bf16(const float* in, bf16* out, long long rows, int C, int drop_first_of, cudaStream_t stream);
+int launch_cast_f32_bf16(const float* in, bf16* out, long long rows, int C, int drop_first_of, cudaStream_t stream,
+                         int split = 0);
 int launch_fill_pose_token(float* x, const float* tok, int samples, int tokens_per_sample, int C,
                            cudaStream_t stream);
-int launch_upsample2x(const bf16* in, bf16* out, int nimg, int H, int W, int C, int OH, int OW, cudaStream_t stream);
+int launch_upsample2x(const bf16* in, bf16* out, int nimg, int H, int W, int C, int OH, int OW, cudaStream_t stream,
+                      int split = 0);
 int launch_rope2d(bf16* tokens, const long long* pos, int B, int N, int H, cudaStream_t stream);
 // preprocess.cu: SLAM_image_only.process_image on the device (PIL-exact Lanczos resize + ToTensor/Normalize/Grayscale)
 int launch_preprocess_rgb8(const uint8_t* rgb_dev, int H, int W, int res_w, int res_h, int w_edge, int h_edge,

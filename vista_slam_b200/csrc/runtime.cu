@@ -20,33 +20,43 @@ namespace sta {
 // ---------------------------------------------------------------------------
 // weight packing kernels (run once per tensor at load time)
 // ---------------------------------------------------------------------------
-// dst[r * ldd + c] = bf16(src[r * cols + c])
+// dst[r * ldd + c] = bf16(src[r * cols + c]).  Split-precision mode (common.cuh): a weight row of logical width kw
+// is stored as (hi | hi | lo), each part kw wide (ldd = 3 * kw).
+__device__ __forceinline__ void put_weight(__nv_bfloat16* d, float v, int split, long long kw) {
+  const __nv_bfloat16 hi = __float2bfloat16(v);
+  d[0] = hi;
+  if (split) {
+    d[kw] = hi;
+    d[2 * kw] = __float2bfloat16(v - __bfloat162float(hi));
+  }
+}
 __global__ void pack_linear_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols,
-                                   long long ldd) {
+                                   long long ldd, int split) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(rows) * cols) return;
   const int r = static_cast<int>(idx / cols), c = static_cast<int>(idx % cols);
-  dst[r * ldd + c] = __float2bfloat16(src[idx]);
+  put_weight(dst + r * ldd + c, src[idx], split, ldd / 3);
 }
-// Conv2d weight [Cout][Cin][3][3] -> [Cout][(kh*3+kw)][Cin_pad]
+// Conv2d weight [Cout][Cin][3][3] -> [Cout][(kh*3+kw)][Cin_pad]  (split mode: [..][3 * Cin_pad] = hi | hi | lo per tap)
 __global__ void pack_conv3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cout, int Cin,
-                                  int Cin_pad) {
+                                  int Cin_pad, int split) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(Cout) * Cin * 9) return;
   const int tap = static_cast<int>(idx % 9);
   const int ci = static_cast<int>((idx / 9) % Cin);
   const int co = static_cast<int>(idx / (9LL * Cin));
-  dst[(static_cast<long long>(co) * 9 + tap) * Cin_pad + ci] = __float2bfloat16(src[idx]);
+  put_weight(dst + (static_cast<long long>(co) * 9 + tap) * (split ? 3 * Cin_pad : Cin_pad) + ci, src[idx], split, Cin_pad);
 }
 // ConvTranspose2d weight [Cin][Cout][k][k] -> [(kh*k+kw)*Cout_pad + co][Cin_pad]
 __global__ void pack_convT_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cin, int Cout,
-                                  int k, int Cin_pad, int Cout_pad) {
+                                  int k, int Cin_pad, int Cout_pad, int split) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(Cin) * Cout * k * k) return;
   const int kk = static_cast<int>(idx % (k * k));
   const int co = static_cast<int>((idx / (k * k)) % Cout);
   const int ci = static_cast<int>(idx / (static_cast<long long>(k) * k * Cout));
-  dst[(static_cast<long long>(kk) * Cout_pad + co) * Cin_pad + ci] = __float2bfloat16(src[idx]);
+  put_weight(dst + (static_cast<long long>(kk) * Cout_pad + co) * (split ? 3 * Cin_pad : Cin_pad) + ci, src[idx], split,
+             Cin_pad);
 }
 // [rows][cols] fp32 -> [cols][rows] fp32
 __global__ void transpose_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
@@ -108,7 +118,7 @@ layernorm_f32_kernel(const float* __restrict__ x, int rows, int C, float eps, co
 struct Lin {
   bf16* w = nullptr;  // [N][K]
   float* b = nullptr; // [N] or null
-  int N = 0, K = 0;
+  int N = 0, K = 0;   // K is the PHYSICAL reduction length: 3 x the logical one in split-precision mode
 };
 struct LNp {
   float *g = nullptr, *b = nullptr;
@@ -144,6 +154,7 @@ struct Workspace {
   size_t bytes = 0;
   size_t off = 0;
   int nimg = 0, h = 0, w = 0;
+  int bmul = 1;  // bf16 activations are 3x wide in split-precision mode
   template <typename T>
   T* take(size_t n) {
     off = (off + 255) & ~static_cast<size_t>(255);
@@ -151,6 +162,7 @@ struct Workspace {
     off += n * sizeof(T);
     return p;
   }
+  bf16* takeb(size_t n) { return take<bf16>(n * bmul); }  // bf16 activation buffer with n LOGICAL elements
 };
 
 }  // namespace sta
@@ -158,6 +170,11 @@ struct Workspace {
 using namespace sta;
 
 struct StaModel {
+  // Precision of the tensor-core operands: 0 = bf16 (production), 1 = split-precision "x3" parity mode -- every bf16
+  // activation is (hi | lo | hi), every bf16 weight (hi | hi | lo) (common.cuh), the same gemm_tc_kernel mainloop runs
+  // over 3K, attention runs in fp32 on the CUDA cores.  ~17 significant operand bits instead of 8; ~3.5x slower.
+  int split = 0;
+  int bmul() const { return split ? 3 : 1; }
   // ---- weights ----
   char* arena = nullptr;
   size_t arena_bytes = 0, arena_off = 0;
@@ -255,10 +272,10 @@ void reg_linear(StaModel* m, const std::string& prefix, Lin* L, int N, int K, bo
                 std::vector<int64_t> wshape = {}) {
   const int Np = N_pad > 0 ? N_pad : N;
   L->N = Np;
-  L->K = K;
-  L->w = m->alloc<bf16>(static_cast<size_t>(Np) * K);
+  L->K = K * m->bmul();
+  L->w = m->alloc<bf16>(static_cast<size_t>(Np) * L->K);
   if (wshape.empty()) wshape = {N, K};
-  add_slot(m, prefix + ".weight", PK_LINEAR, wshape, L->w, K);
+  add_slot(m, prefix + ".weight", PK_LINEAR, wshape, L->w, L->K);
   if (bias) {
     L->b = m->alloc<float>(Np);
     add_slot(m, prefix + ".bias", PK_F32, {N}, L->b);
@@ -273,8 +290,8 @@ void reg_ln(StaModel* m, const std::string& prefix, LNp* p, int C) {
 void reg_conv3(StaModel* m, const std::string& prefix, Lin* L, int Cout, int Cin, bool bias, int Cin_pad = 0) {
   const int Cp = Cin_pad > 0 ? Cin_pad : Cin;
   L->N = Cout;
-  L->K = 9 * Cp;
-  L->w = m->alloc<bf16>(static_cast<size_t>(Cout) * 9 * Cp);
+  L->K = 9 * Cp * m->bmul();
+  L->w = m->alloc<bf16>(static_cast<size_t>(Cout) * L->K);
   add_slot(m, prefix + ".weight", PK_CONV3, {Cout, Cin, 3, 3}, L->w, 0, Cp);
   if (bias) {
     L->b = m->alloc<float>(Cout);
@@ -283,7 +300,7 @@ void reg_conv3(StaModel* m, const std::string& prefix, Lin* L, int Cout, int Cin
 }
 void reg_convT(StaModel* m, const std::string& prefix, Lin* L, int C, int k, int C_pad) {
   L->N = k * k * C_pad;
-  L->K = C_pad;
+  L->K = C_pad * m->bmul();
   L->w = m->alloc<bf16>(static_cast<size_t>(L->N) * L->K);
   add_slot(m, prefix + ".weight", PK_CONVT, {C, C, k, k}, L->w, 0, C_pad, C_pad, k);
   L->b = m->alloc<float>(C_pad);  // indexed by output channel
@@ -321,13 +338,13 @@ int build_registry(StaModel* m) {
     reg_linear(m, p + "cross_attn.projq", &b.cq, kDecDim, kDecDim);
     // projk and projv are fused into one [1536][768] matrix (both act on norm_y(y))
     b.ckv.N = 2 * kDecDim;
-    b.ckv.K = kDecDim;
-    b.ckv.w = m->alloc<bf16>(static_cast<size_t>(2) * kDecDim * kDecDim);
+    b.ckv.K = kDecDim * m->bmul();
+    b.ckv.w = m->alloc<bf16>(static_cast<size_t>(2) * kDecDim * b.ckv.K);
     b.ckv.b = m->alloc<float>(2 * kDecDim);
-    add_slot(m, p + "cross_attn.projk.weight", PK_LINEAR, {kDecDim, kDecDim}, b.ckv.w, kDecDim);
+    add_slot(m, p + "cross_attn.projk.weight", PK_LINEAR, {kDecDim, kDecDim}, b.ckv.w, b.ckv.K);
     add_slot(m, p + "cross_attn.projk.bias", PK_F32, {kDecDim}, b.ckv.b);
     add_slot(m, p + "cross_attn.projv.weight", PK_LINEAR, {kDecDim, kDecDim},
-             b.ckv.w + static_cast<size_t>(kDecDim) * kDecDim, kDecDim);
+             b.ckv.w + static_cast<size_t>(kDecDim) * b.ckv.K, b.ckv.K);
     add_slot(m, p + "cross_attn.projv.bias", PK_F32, {kDecDim}, b.ckv.b + kDecDim);
     reg_linear(m, p + "cross_attn.proj", &b.cproj, kDecDim, kDecDim);
     reg_ln(m, p + "norm2", &b.n2, kDecDim);
@@ -439,6 +456,8 @@ int gemm(const Ctx& c, int amode, int epi, const bf16* A, long long lda, const L
   p.N = L.N;
   p.K = L.K;
   if (!p.bias) p.bias = L.b;
+  p.split = c.m->split;
+  if (p.split && (epi == EPI_BF16 || epi == EPI_GELU || epi == EPI_ROPE)) p.ldo *= 3;  // (hi | lo | hi) output rows
   g.p = p;
   c.m->launches++;
   const double rows = (amode == A_CONV3) ? static_cast<double>(p.nimg) * p.H * p.W : static_cast<double>(p.M);
@@ -472,7 +491,7 @@ int conv3(const Ctx& c, const bf16* in, int nimg, int H, int W, int Cin, const L
   p.nimg = nimg;
   p.H = H;
   p.W = W;
-  p.Cin = Cin;
+  p.Cin = Cin * c.m->bmul();  // physical channels of the NHWC input
   p.out = out;
   p.out2 = out_relu;
   p.ldo = L.N;
@@ -486,19 +505,21 @@ int ln(const Ctx& c, const float* x, int rows, int C, const LNp& a, bf16* out1, 
   c.m->launches++;
   ProfScope ps(c, PROF_LN, 0.0);
   return launch_layernorm(x, rows, C, kLnEps, a.g, a.b, out1, b2 ? b2->g : nullptr, b2 ? b2->b : nullptr, out2,
-                          drop_first_of, c.st);
+                          drop_first_of, c.st, c.m->split);
 }
 int attn(const Ctx& c, const bf16* q, long long ldq, int qc, const bf16* k, long long ldk, int kc, const bf16* v,
          long long ldv, int vc, bf16* out, long long ldo, int batch, int heads, int nq, int nk, int shift,
          int split_first_row = 0) {
   AttnLaunch a;
-  a.q = q; a.ldq = ldq; a.q_col0 = qc;
-  a.k = k; a.ldk = ldk; a.k_col0 = kc;
-  a.v = v; a.ldv = ldv; a.v_col0 = vc;
-  a.out = out; a.ldo = ldo;
+  const int bm = c.m->bmul();  // the ld* arguments are logical widths
+  a.q = q; a.ldq = ldq * bm; a.q_col0 = qc;
+  a.k = k; a.ldk = ldk * bm; a.k_col0 = kc;
+  a.v = v; a.ldv = ldv * bm; a.v_col0 = vc;
+  a.out = out; a.ldo = ldo * bm;
   a.batch = batch; a.heads = heads; a.nq = nq; a.nk = nk;
   a.kv_batch_shift = shift;
   a.split_first_row = split_first_row;
+  a.split = c.m->split;
   a.scale = 0.125f;  // head_dim ** -0.5, sta_blocks.py:86
   c.m->launches++;
   ProfScope ps(c, PROF_ATTN, 4.0 * batch * heads * static_cast<double>(nq) * nk * 64);
@@ -530,7 +551,8 @@ struct DptBufs {
   bf16 *hc1, *hup;
 };
 
-size_t ws_need(int nimg, int h, int w) {
+size_t ws_need(int nimg, int h, int w, int bmul = 1) {
+  if (bmul > 1) return ws_need(nimg, h, w) * bmul;  // split-precision mode: bf16 buffers are 3x wide (fp32 ones over-counted)
   const size_t N = static_cast<size_t>(h) * w, T = nimg * N, Td = nimg * (N + 1);
   size_t b = 0;
   auto add = [&](size_t n) { b += ((n + 255) / 256) * 256 + 256; };
@@ -558,7 +580,8 @@ size_t ws_need(int nimg, int h, int w) {
 void drop_graphs(StaModel* m);
 
 int ensure_ws(StaModel* m, int nimg, int h, int w) {
-  const size_t need = ws_need(nimg, h, w);
+  const size_t need = ws_need(nimg, h, w, m->bmul());
+  m->ws.bmul = m->bmul();
   if (m->ws.bytes < need) {
     STA_CHECK_CUDA(cudaDeviceSynchronize());
     drop_graphs(m);  // they point into the old workspace
@@ -670,11 +693,11 @@ int run_encoder(const Ctx& c, int nimg, int N, float* x, EncBufs& e) {
 EncBufs take_enc(Workspace& ws, int nimg, int N) {
   const size_t T = static_cast<size_t>(nimg) * N;
   EncBufs e;
-  e.patches = ws.take<bf16>(T * 768);
-  e.lnb = ws.take<bf16>(T * 1024);
-  e.qkv = ws.take<bf16>(T * 3072);
-  e.att = ws.take<bf16>(T * 1024);
-  e.hid = ws.take<bf16>(T * 4096);
+  e.patches = ws.takeb(T * 768);
+  e.lnb = ws.takeb(T * 1024);
+  e.qkv = ws.takeb(T * 3072);
+  e.att = ws.takeb(T * 1024);
+  e.hid = ws.takeb(T * 4096);
   e.pos = ws.take<int>(T * 2);
   return e;
 }
@@ -682,15 +705,15 @@ DecBufs take_dec(Workspace& ws, int S, int N) {
   const size_t T = static_cast<size_t>(S) * N, Td = static_cast<size_t>(S) * (N + 1);
   DecBufs d;
   d.xd = ws.take<float>(Td * 768);
-  d.enc_bf16 = ws.take<bf16>(T * 1024);
-  d.ln1 = ws.take<bf16>(Td * 768);
-  d.lny = ws.take<bf16>(Td * 768);
-  d.qkv = ws.take<bf16>(Td * 2304);
-  d.att = ws.take<bf16>(Td * 768);
-  d.qc = ws.take<bf16>(Td * 768);
-  d.kvc = ws.take<bf16>(Td * 1536);
-  d.hid = ws.take<bf16>(Td * 3072);
-  for (int i = 0; i < 3; ++i) d.hook[i] = ws.take<bf16>(T * 768);
+  d.enc_bf16 = ws.takeb(T * 1024);
+  d.ln1 = ws.takeb(Td * 768);
+  d.lny = ws.takeb(Td * 768);
+  d.qkv = ws.takeb(Td * 2304);
+  d.att = ws.takeb(Td * 768);
+  d.qc = ws.takeb(Td * 768);
+  d.kvc = ws.takeb(Td * 1536);
+  d.hid = ws.takeb(Td * 3072);
+  for (int i = 0; i < 3; ++i) d.hook[i] = ws.takeb(T * 768);
   d.pos = ws.take<int>(Td * 2);
   return d;
 }
@@ -744,7 +767,7 @@ int run_decoder(const Ctx& c, int B, int N, DecBufs& d, float* const* out1, floa
     RUN(linear(c, EPI_F32, d.hid, Td, b.fc2, d.xd, d.xd));
     if (l + 1 == 6 || l + 1 == 9) {  // DPT hooks [0, 7, 10, 13] -> decoder outputs 6, 9, 12 (dpt_head.py:112)
       m->launches++;
-      RUN(launch_cast_f32_bf16(d.xd, d.hook[l + 1 == 6 ? 0 : 1], Td, kDecDim, M, c.st));
+      RUN(launch_cast_f32_bf16(d.xd, d.hook[l + 1 == 6 ? 0 : 1], Td, kDecDim, M, c.st, m->split));
     }
     if (l + 1 < 12) RUN(emit(l + 1));
   }
@@ -778,46 +801,46 @@ int run_dpt(const Ctx& c, Workspace& ws, int nimg, int h, int w, const bf16* hoo
   const int h4 = (h + 1) / 2, w4 = (w + 1) / 2;
   const int LH[4] = {4 * h, 2 * h, h, h4}, LW[4] = {4 * w, 2 * w, w, w4};
   DptBufs b;
-  b.a0 = ws.take<bf16>(static_cast<size_t>(T) * 128);
-  b.l1 = ws.take<bf16>(static_cast<size_t>(nimg) * 16 * N * 128);
-  b.a1 = ws.take<bf16>(static_cast<size_t>(T) * 192);
-  b.l2 = ws.take<bf16>(static_cast<size_t>(nimg) * 4 * N * 192);
-  b.l3 = ws.take<bf16>(static_cast<size_t>(T) * 384);
-  b.a3 = ws.take<bf16>(static_cast<size_t>(T) * 768);
-  b.col4 = ws.take<bf16>(static_cast<size_t>(nimg) * h4 * w4 * 6912);
-  b.l4 = ws.take<bf16>(static_cast<size_t>(nimg) * h4 * w4 * 768);
+  b.a0 = ws.takeb(static_cast<size_t>(T) * 128);
+  b.l1 = ws.takeb(static_cast<size_t>(nimg) * 16 * N * 128);
+  b.a1 = ws.takeb(static_cast<size_t>(T) * 192);
+  b.l2 = ws.takeb(static_cast<size_t>(nimg) * 4 * N * 192);
+  b.l3 = ws.takeb(static_cast<size_t>(T) * 384);
+  b.a3 = ws.takeb(static_cast<size_t>(T) * 768);
+  b.col4 = ws.takeb(static_cast<size_t>(nimg) * h4 * w4 * 6912);
+  b.l4 = ws.takeb(static_cast<size_t>(nimg) * h4 * w4 * 768);
   for (int i = 0; i < 4; ++i) {
-    b.r_raw[i] = ws.take<bf16>(static_cast<size_t>(nimg) * LH[i] * LW[i] * 256);
-    b.r_relu[i] = ws.take<bf16>(static_cast<size_t>(nimg) * LH[i] * LW[i] * 256);
+    b.r_raw[i] = ws.takeb(static_cast<size_t>(nimg) * LH[i] * LW[i] * 256);
+    b.r_relu[i] = ws.takeb(static_cast<size_t>(nimg) * LH[i] * LW[i] * 256);
   }
   const size_t big = static_cast<size_t>(nimg) * 16 * N * 256;
-  b.t1 = ws.take<bf16>(big);
-  b.t2 = ws.take<bf16>(big);
-  b.s_raw = ws.take<bf16>(big);
-  b.s_relu = ws.take<bf16>(big);
-  b.o = ws.take<bf16>(big);
-  b.up = ws.take<bf16>(static_cast<size_t>(nimg) * 64 * N * 256);
-  b.path = ws.take<bf16>(static_cast<size_t>(nimg) * 64 * N * 256);
-  b.hc1 = ws.take<bf16>(static_cast<size_t>(nimg) * 64 * N * 128);
-  b.hup = ws.take<bf16>(static_cast<size_t>(nimg) * 256 * N * 128);
+  b.t1 = ws.takeb(big);
+  b.t2 = ws.takeb(big);
+  b.s_raw = ws.takeb(big);
+  b.s_relu = ws.takeb(big);
+  b.o = ws.takeb(big);
+  b.up = ws.takeb(static_cast<size_t>(nimg) * 64 * N * 256);
+  b.path = ws.takeb(static_cast<size_t>(nimg) * 64 * N * 256);
+  b.hc1 = ws.takeb(static_cast<size_t>(nimg) * 64 * N * 128);
+  b.hup = ws.takeb(static_cast<size_t>(nimg) * 256 * N * 128);
 
   // ---- act_postprocess (dpt_block.py:356-410) ----
   RUN(linear(c, EPI_BF16, hook0, T, m->act0, b.a0));
   {
     GemmParams p = {};
     p.M = T; p.out = b.l1; p.ps_k = 4; p.ps_cout = 128; p.ps_h = h; p.ps_w = w;
-    RUN(gemm(c, A_LINEAR, EPI_PIXSHUF, b.a0, 128, m->act0T, p));
+    RUN(gemm(c, A_LINEAR, EPI_PIXSHUF, b.a0, m->act0T.K, m->act0T, p));
   }
   RUN(linear(c, EPI_BF16, hook1, T, m->act1, b.a1));
   {
     GemmParams p = {};
     p.M = T; p.out = b.l2; p.ps_k = 2; p.ps_cout = 192; p.ps_h = h; p.ps_w = w;
-    RUN(gemm(c, A_LINEAR, EPI_PIXSHUF, b.a1, 192, m->act1T, p));
+    RUN(gemm(c, A_LINEAR, EPI_PIXSHUF, b.a1, m->act1T.K, m->act1T, p));
   }
   RUN(linear(c, EPI_BF16, hook2, T, m->act2, b.l3));
   RUN(linear(c, EPI_BF16, hook3, T, m->act3, b.a3));
   m->launches++;
-  RUN(launch_im2col_3x3_s2(b.a3, b.col4, nimg, h, w, 768, c.st));
+  RUN(launch_im2col_3x3_s2(b.a3, b.col4, nimg, h, w, 768 * m->bmul(), c.st));  // pure channel-vector copy
   RUN(linear(c, EPI_BF16, b.col4, nimg * h4 * w4, m->act3c, b.l4));
   // ---- layer_rn: 3x3 conv to 256 channels, no bias (dpt_block.py:33-75); raw + relu copies ----
   const bf16* lin[4] = {b.l1, b.l2, b.l3, b.l4};
@@ -853,17 +876,17 @@ int run_dpt(const Ctx& c, Workspace& ws, int nimg, int h, int w, const bf16* hoo
     if (lvl == 3) { OH = LH[2]; OW = LW[2]; }
     RUN(linear(c, EPI_BF16, b.o, nimg * Hh * Ww, r.out, b.up));
     m->launches++;
-    RUN(launch_upsample2x(b.up, b.path, nimg, Hh, Ww, 256, OH, OW, c.st));
+    RUN(launch_upsample2x(b.up, b.path, nimg, Hh, Ww, 256, OH, OW, c.st, m->split));
     path = b.path;
   }
   // ---- head (dpt_block.py:318-324) + postprocess (postprocess.py:10-62) ----
   const int H8 = 8 * h, W8 = 8 * w;
   RUN(conv3(c, b.path, nimg, H8, W8, 256, m->head0, b.hc1, nullptr, nullptr, nullptr, 0));
   m->launches++;
-  RUN(launch_upsample2x(b.hc1, b.hup, nimg, H8, W8, 128, 2 * H8, 2 * W8, c.st));
+  RUN(launch_upsample2x(b.hc1, b.hup, nimg, H8, W8, 128, 2 * H8, 2 * W8, c.st, m->split));
   {
     GemmParams p = {};
-    p.nimg = nimg; p.H = 2 * H8; p.W = 2 * W8; p.Cin = 128;
+    p.nimg = nimg; p.H = 2 * H8; p.W = 2 * W8; p.Cin = 128 * m->bmul();
     p.head_w = m->head4_w; p.head_b = m->head4_b; p.pts3d = pts3d; p.conf = conf;
     RUN(gemm(c, A_CONV3, EPI_HEAD, b.hup, 0, m->head2, p));
   }
@@ -896,12 +919,13 @@ int forward_chunk(const Ctx& c, const void* img1, const void* img2, int img_is_b
   DecBufs d = take_dec(ws, S, N);
   // encode both views as one batch of 2B images: [view 1 batch ; view 2 batch]
   m->launches += 3;
-  RUN(launch_patch_im2col(img1, img_is_bf16, B, H, W, e.patches, c.st));
-  RUN(launch_patch_im2col(img2, img_is_bf16, B, H, W, e.patches + static_cast<size_t>(B) * N * 768, c.st));
+  const size_t bm = m->bmul();  // physical / logical width of the bf16 activation rows
+  RUN(launch_patch_im2col(img1, img_is_bf16, B, H, W, e.patches, c.st, m->split));
+  RUN(launch_patch_im2col(img2, img_is_bf16, B, H, W, e.patches + static_cast<size_t>(B) * N * 768 * bm, c.st, m->split));
   RUN(launch_make_positions(e.pos, S, h, w, 0, c.st));
   RUN(run_encoder(c, S, N, x, e));
   m->launches += 2;
-  RUN(launch_cast_f32_bf16(x, d.enc_bf16, static_cast<long long>(S) * N, kEncDim, 0, c.st));
+  RUN(launch_cast_f32_bf16(x, d.enc_bf16, static_cast<long long>(S) * N, kEncDim, 0, c.st, m->split));
   RUN(launch_make_positions(d.pos, S, h, w, 1, c.st));
   RUN(run_decoder(c, B, N, d, nullptr, nullptr));
   // pose heads on the (dec_norm-ed) pose tokens of both views
@@ -922,8 +946,8 @@ int forward_chunk(const Ctx& c, const void* img1, const void* img2, int img_is_b
       const int i0 = hf * (B / halves), nb = (hf == halves - 1) ? B - i0 : B / halves;
       const size_t save = ws.off;
       const size_t tok0 = (static_cast<size_t>(v) * B + i0) * N;
-      RUN(run_dpt(c, ws, nb, h, w, d.enc_bf16 + tok0 * 1024, d.hook[0] + tok0 * 768, d.hook[1] + tok0 * 768,
-                  d.hook[2] + tok0 * 768, pts3d + (static_cast<long long>(v) * B_total + i0) * px * 3,
+      RUN(run_dpt(c, ws, nb, h, w, d.enc_bf16 + tok0 * 1024 * bm, d.hook[0] + tok0 * 768 * bm, d.hook[1] + tok0 * 768 * bm,
+                  d.hook[2] + tok0 * 768 * bm, pts3d + (static_cast<long long>(v) * B_total + i0) * px * 3,
                   conf + (static_cast<long long>(v) * B_total + i0) * px));
       ws.off = save;
       if (ev_parts) STA_CHECK_CUDA(cudaEventRecord(ev_parts[v * 2 + hf], c.st));
@@ -947,7 +971,13 @@ int sta_device_synchronize(void) {
   return 0;
 }
 
-int sta_create(StaModel** out) {
+int sta_create(StaModel** out) { return sta_create_ex(out, STA_PRECISION_BF16); }
+
+int sta_create_ex(StaModel** out, int precision) {
+  if (precision != STA_PRECISION_BF16 && precision != STA_PRECISION_X3) {
+    set_last_error("sta_create_ex: unknown precision (0 = bf16, 1 = split-precision x3 parity mode)");
+    return 2;
+  }
   if (!out) {
     set_last_error("sta_create: null output pointer");
     return 2;
@@ -965,7 +995,9 @@ int sta_create(StaModel** out) {
     return 3;
   }
   StaModel* m = new StaModel();
-  m->arena_bytes = static_cast<size_t>(960) << 20;  // 438.5 M params: ~877 MB bf16 + fp32 vectors + padding
+  m->split = (precision == STA_PRECISION_X3) ? 1 : 0;
+  // 438.5 M params: ~877 MB bf16 + fp32 vectors + padding (3x the bf16 part in split-precision mode)
+  m->arena_bytes = static_cast<size_t>(m->split ? 2800 : 960) << 20;
   cudaError_t e = cudaMalloc(&m->arena, m->arena_bytes);
   if (e != cudaSuccess) {
     set_last_error(std::string("cudaMalloc(weight arena) failed: ") + cudaGetErrorString(e));
@@ -1115,16 +1147,16 @@ int sta_load_tensor(StaModel* m, const char* name, const float* data, const int6
     case PK_LINEAR: {
       const int rows = static_cast<int>(s.shape[0]);
       const int cols = static_cast<int>(numel / rows);
-      pack_linear_kernel<<<blocks, threads>>>(src, static_cast<bf16*>(s.dst), rows, cols, s.ldd);
+      pack_linear_kernel<<<blocks, threads>>>(src, static_cast<bf16*>(s.dst), rows, cols, s.ldd, m->split);
       break;
     }
     case PK_CONV3:
       pack_conv3_kernel<<<blocks, threads>>>(src, static_cast<bf16*>(s.dst), static_cast<int>(s.shape[0]),
-                                             static_cast<int>(s.shape[1]), s.cin_pad);
+                                             static_cast<int>(s.shape[1]), s.cin_pad, m->split);
       break;
     case PK_CONVT:
       pack_convT_kernel<<<blocks, threads>>>(src, static_cast<bf16*>(s.dst), static_cast<int>(s.shape[0]),
-                                             static_cast<int>(s.shape[1]), s.k, s.cin_pad, s.cout_pad);
+                                             static_cast<int>(s.shape[1]), s.k, s.cin_pad, s.cout_pad, m->split);
       break;
     case PK_TRANSPOSE_F32:
       transpose_f32_kernel<<<blocks, threads>>>(src, static_cast<float*>(s.dst), static_cast<int>(s.shape[0]),
@@ -1152,7 +1184,7 @@ int sta_encode(StaModel* m, const void* img_dev, int img_is_bf16, int B, int H, 
   RUN(ensure_ws(m, B, h, w));
   EncBufs e = take_enc(m->ws, B, N);
   m->launches += 1;
-  RUN(launch_patch_im2col(img_dev, img_is_bf16, B, H, W, e.patches, c.st));
+  RUN(launch_patch_im2col(img_dev, img_is_bf16, B, H, W, e.patches, c.st, m->split));
   // launch-bound sizes: the encoder proper is replayed as a CUDA graph on workspace buffers, the features are
   // then copied to the caller's tensor (which is long-lived: slam.py:145 keeps it for the whole run)
   const bool graphed = static_cast<long long>(B) * N <= kGraphMaxTokens;
@@ -1188,9 +1220,9 @@ int sta_decode(StaModel* m, const float* feat1_dev, const float* feat2_dev, cons
   RUN(ensure_ws(m, 2 * B, N, 1));
   DecBufs d = take_dec(m->ws, 2 * B, N);
   m->launches += 3;
-  RUN(launch_cast_f32_bf16(feat1_dev, d.enc_bf16, static_cast<long long>(B) * N, kEncDim, 0, c.st));
-  RUN(launch_cast_f32_bf16(feat2_dev, d.enc_bf16 + static_cast<size_t>(B) * N * kEncDim, static_cast<long long>(B) * N,
-                           kEncDim, 0, c.st));
+  RUN(launch_cast_f32_bf16(feat1_dev, d.enc_bf16, static_cast<long long>(B) * N, kEncDim, 0, c.st, m->split));
+  RUN(launch_cast_f32_bf16(feat2_dev, d.enc_bf16 + static_cast<size_t>(B) * N * kEncDim * m->bmul(),
+                           static_cast<long long>(B) * N, kEncDim, 0, c.st, m->split));
   {
     const long long total = 2LL * B * (N + 1);
     build_dec_pos_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, c.st>>>(
@@ -1217,15 +1249,15 @@ int sta_head_pts(StaModel* m, const float* enc_feat_dev, const float* dec6_dev, 
   RUN(ensure_ws(m, B, h, w));
   Workspace& ws = m->ws;
   const size_t T = static_cast<size_t>(B) * N;
-  bf16* k0 = ws.take<bf16>(T * 1024);
-  bf16* k1 = ws.take<bf16>(T * 768);
-  bf16* k2 = ws.take<bf16>(T * 768);
-  bf16* k3 = ws.take<bf16>(T * 768);
+  bf16* k0 = ws.takeb(T * 1024);
+  bf16* k1 = ws.takeb(T * 768);
+  bf16* k2 = ws.takeb(T * 768);
+  bf16* k3 = ws.takeb(T * 768);
   m->launches += 4;
-  RUN(launch_cast_f32_bf16(enc_feat_dev, k0, T, 1024, 0, c.st));
-  RUN(launch_cast_f32_bf16(dec6_dev, k1, T, 768, 0, c.st));
-  RUN(launch_cast_f32_bf16(dec9_dev, k2, T, 768, 0, c.st));
-  RUN(launch_cast_f32_bf16(dec12_dev, k3, T, 768, 0, c.st));
+  RUN(launch_cast_f32_bf16(enc_feat_dev, k0, T, 1024, 0, c.st, m->split));
+  RUN(launch_cast_f32_bf16(dec6_dev, k1, T, 768, 0, c.st, m->split));
+  RUN(launch_cast_f32_bf16(dec9_dev, k2, T, 768, 0, c.st, m->split));
+  RUN(launch_cast_f32_bf16(dec12_dev, k3, T, 768, 0, c.st, m->split));
   return run_dpt(c, ws, B, h, w, k0, k1, k2, k3, pts3d_out_dev, conf_out_dev);
 }
 
@@ -1269,9 +1301,10 @@ int sta_regress_pairs(StaModel* m, const float* feat_i_dev, const float* feat_j_
     }
   }
   m->launches += 2;
-  RUN(launch_cast_f32_bf16(feat_i_dev, d.enc_bf16, static_cast<long long>(K) * N, kEncDim, 0, c.st));
-  RUN(launch_cast_f32_bf16(feat_j_dev, d.enc_bf16 + static_cast<size_t>(K) * N * kEncDim, static_cast<long long>(K) * N,
-                           kEncDim, 0, c.st));
+  const size_t bm = m->bmul();
+  RUN(launch_cast_f32_bf16(feat_i_dev, d.enc_bf16, static_cast<long long>(K) * N, kEncDim, 0, c.st, m->split));
+  RUN(launch_cast_f32_bf16(feat_j_dev, d.enc_bf16 + static_cast<size_t>(K) * N * kEncDim * bm, static_cast<long long>(K) * N,
+                           kEncDim, 0, c.st, m->split));
   auto body = [&](const Ctx& cc) -> int {
     m->launches += 3;
     RUN(launch_make_positions(d.pos, S, h, w, 1, cc.st));
@@ -1282,8 +1315,8 @@ int sta_regress_pairs(StaModel* m, const float* feat_i_dev, const float* feat_j_
     for (int v = 0; v < 2; ++v) {
       const size_t save = ws.off;
       const size_t tok0 = static_cast<size_t>(v) * K * N;
-      RUN(run_dpt(cc, ws, K, h, w, d.enc_bf16 + tok0 * 1024, d.hook[0] + tok0 * 768, d.hook[1] + tok0 * 768,
-                  d.hook[2] + tok0 * 768, o_pts + static_cast<long long>(v) * K * px * 3,
+      RUN(run_dpt(cc, ws, K, h, w, d.enc_bf16 + tok0 * 1024 * bm, d.hook[0] + tok0 * 768 * bm, d.hook[1] + tok0 * 768 * bm,
+                  d.hook[2] + tok0 * 768 * bm, o_pts + static_cast<long long>(v) * K * px * 3,
                   o_conf + static_cast<long long>(v) * K * px));
       ws.off = save;
     }
@@ -1477,6 +1510,7 @@ int sta_op_gemm(const StaGemmDesc* d, void* stream) {
   }
   p.ps_k = d->ps_k; p.ps_cout = d->ps_cout; p.ps_h = d->ps_h; p.ps_w = d->ps_w;
   p.head_w = d->head_w; p.head_b = d->head_b; p.pts3d = d->pts3d; p.conf = d->conf;
+  p.split = d->split_precision;
   g.p = p;
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }

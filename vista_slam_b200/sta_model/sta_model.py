@@ -133,8 +133,13 @@ class SymmetricTwoViewAssociation(nn.Module):
     def __init__(self, img_size=(224, 224), patch_size=16, enc_embed_dim=1024, enc_depth=24, enc_num_heads=16,
                  dec_embed_dim=768, dec_depth=12, dec_num_heads=12, mlp_ratio=4, norm_layer=None, pos_embed="RoPE100",
                  output_mode="pts3d", head_type="dpt", depth_mode=("exp", -inf, inf), conf_mode=("exp", 1, inf),
-                 freeze="none", landscape_only=True, patch_embed_cls="PatchEmbedDust3R"):
+                 freeze="none", landscape_only=True, patch_embed_cls="PatchEmbedDust3R", precision="bf16"):
         super().__init__()
+        # `precision` is the one extension of the reference signature: "bf16" (production; every benchmark number)
+        # or "x3" = split-precision parity mode (include/sta_b200.h, STA_PRECISION_X3) used by the parity tests.
+        if precision not in ("bf16", "x3"):
+            raise ValueError("precision must be 'bf16' or 'x3'")
+        self.precision = precision
         fixed = dict(patch_size=(patch_size, 16), enc_embed_dim=(enc_embed_dim, 1024), enc_depth=(enc_depth, 24),
                      enc_num_heads=(enc_num_heads, 16), dec_embed_dim=(dec_embed_dim, 768), dec_depth=(dec_depth, 12),
                      dec_num_heads=(dec_num_heads, 12), mlp_ratio=(mlp_ratio, 4), pos_embed=(pos_embed, "RoPE100"),
@@ -231,9 +236,7 @@ class SymmetricTwoViewAssociation(nn.Module):
             return L
         with torch.cuda.device(like.device):
             if self._handle is None:
-                h = ctypes.c_void_p()
-                _lib.check(L.sta_create(ctypes.byref(h)), "sta_create")
-                self._handle = h
+                self._handle = self._create(L)
             for name, t in self.state_dict().items():
                 src = t.detach()
                 on_dev = 1 if src.is_cuda else 0
@@ -246,6 +249,12 @@ class SymmetricTwoViewAssociation(nn.Module):
                 raise RuntimeError("%d state-dict tensors missing after upload" % missing)
         self._uploaded_key = key
         return L
+
+    def _create(self, L):
+        h = ctypes.c_void_p()
+        prec = _lib.PRECISION_X3 if self.precision == "x3" else _lib.PRECISION_BF16
+        _lib.check(L.sta_create_ex(ctypes.byref(h), prec), "sta_create_ex")
+        return h
 
     def weight_arena(self):
         """uint8 CUDA tensor aliasing the library's packed-weight arena (for a NCCL broadcast)."""
@@ -271,9 +280,7 @@ class SymmetricTwoViewAssociation(nn.Module):
         else:
             with torch.cuda.device(device):
                 if self._handle is None:
-                    h = ctypes.c_void_p()
-                    _lib.check(L.sta_create(ctypes.byref(h)), "sta_create")
-                    self._handle = h
+                    self._handle = self._create(L)
         with torch.cuda.device(device):
             arena = self.weight_arena()
             dist.broadcast(arena, src=src, group=group)
