@@ -180,6 +180,20 @@ int sta_regress_pairs(StaModel* m, const float* feat_i_dev, const float* feat_j_
                       float* pose_out_dev, float* pose_conf_out_dev, float* pts3d_out_dev, float* conf_out_dev,
                       float* intri_out_dev, float* depth_out_dev, float* conf_mean_out_dev, void* scratch, void* stream);
 
+/* The same step in two phases, keeping the reference's early-out (slam.py:169-170: `rel_pose_conf < thres and i - j != 1`
+ * skips both DPT heads): _begin runs the symmetric decoder and the pose heads for all K candidate edges
+ * (pose_out [2][K][4][4], pose_conf_out [2][K]; block 0 = the i -> j direction) and keeps the decoder hooks in the
+ * handle's workspace; the caller reads the K confidences (ONE device-to-host copy per keyframe instead of one per edge),
+ * and _finish runs the DPT heads + pointmap consumers only for the n_sel surviving edges edge_idx_host[0..n_sel)
+ * (indices into the K candidates; host memory).  Outputs of _finish are compact: pts3d_out [2][n_sel][H][W][3],
+ * conf_out [2][n_sel][H][W], intri_out [n_sel][3][3], depth_out / conf_mean_out optional, scratch for V = 2 n_sel.
+ * No other call on this handle may come between the two phases. */
+int sta_regress_pairs_begin(StaModel* m, const float* feat_i_dev, const float* feat_j_dev, int K, int H, int W,
+                            float* pose_out_dev, float* pose_conf_out_dev, void* stream);
+int sta_regress_pairs_finish(StaModel* m, const int* edge_idx_host, int n_sel, float* pts3d_out_dev, float* conf_out_dev,
+                             float* intri_out_dev, float* depth_out_dev, float* conf_mean_out_dev, void* scratch,
+                             void* stream);
+
 /* Launch-bound sizes (<= 8192 tokens per call: one keyframe, a few edges) of sta_encode and sta_regress_pairs are
  * captured into CUDA graphs per (entry point, batch, H, W) on their second use and replayed afterwards
  * (STA_CUDA_GRAPHS=0 disables).  Number of graph replays so far (tests / diagnostics): */

@@ -368,6 +368,47 @@ class StaOracle:
         pose[:, 3, 3] = 1.0
         return {"pose": pose, "conf": conf.squeeze(-1)}
 
+    def head_pts_ts(self, tokens14, true_shape):
+        """head_pts with the reference's `transpose_to_landscape` wrapper (utils/misc.py:36-82, activate = landscape_only =
+        True): landscape batches run the head at (H, W) = (min, max); all-portrait batches run it at (max, min) on the
+        SAME token sequence and transpose the maps; mixed batches do both per sample."""
+        ts = torch.as_tensor(true_shape)
+        H, W = int(ts.min()), int(ts.max())
+        height, width = ts.T
+        land = width >= height
+
+        def tr(d):
+            return {k: v.swapaxes(1, 2) for k, v in d.items()}
+        if bool(land.all()):
+            return self.head_pts(tokens14, H, W)
+        if bool((~land).all()):
+            return tr(self.head_pts(tokens14, W, H))
+        res_l = self.head_pts([t[land] for t in tokens14], H, W)
+        res_p = tr(self.head_pts([t[~land] for t in tokens14], W, H))
+        out = {}
+        for k in res_l:
+            x = res_l[k].new_empty((len(ts),) + tuple(res_l[k].shape[1:]))
+            x[land] = res_l[k]
+            x[~land] = res_p[k]
+            out[k] = x
+        return out
+
+    def forward_views(self, main_img, main_ts, supports):
+        """forward(views) for any number of support views (sta_model.py:247-291): `supports` = [(img, true_shape)], the
+        neighbour views followed by the loop views (eval mode uses all loop candidates).  Returns (main_res, support_res),
+        two lists of per-support dicts."""
+        mf, mpos = self.encode_image(main_img)
+        main_res, sup_res = [], []
+        for img, ts in supports:
+            nf, npos = self.encode_image(img)
+            md, nd = self.decode_stereo(mf, nf, mpos, npos)
+            for feat, dec, shape, bucket in ((nf, nd, ts, sup_res), (mf, md, main_ts, main_res)):
+                pts = self.head_pts_ts([feat] + [t[:, 1:, :] for t in dec], shape)
+                pose = self.head_pose(dec[-1][:, 0, :])
+                bucket.append({"pts3d_pred": pts["pts3d"], "conf": pts["conf"], "relative_pose": pose["pose"],
+                               "relative_pose_conf": pose["conf"]})
+        return main_res, sup_res
+
     # -- forward(views) with one support view --------------------------------------------------
     def forward_pair(self, img1, img2):
         """forward(), sta_model.py:247-291, main view = img1, one support view = img2.

@@ -80,3 +80,84 @@ def test_keyframe_step_equals_fused_pair_path(cuda_model):
         assert maxn(r["pts3d"][1], sup["pts3d_pred"][b:b + 1]) < 2e-2
         assert maxn(r["pose"], main["relative_pose"][b:b + 1]) < 5e-3
         assert maxn(r["pose_ji"], sup["relative_pose"][b:b + 1]) < 5e-3
+
+
+def test_keyframe_step_vs_oracle_on_the_cached_features(cuda_model, state_dict):
+    """Oracle parity of sta_regress_pairs (not just self-consistency): the cached encoder features go through the oracle's
+    decode_stereo / head_pts / head_pose on the CPU (bf16-operand emulation) and are compared with the batched step."""
+    from oracle.sta_oracle import StaOracle, token_positions
+    from test_model_gpu import TOL_EMU
+    from vista_slam_b200.keyframe import KeyframeFrontend
+    H, W = 64, 80
+    imgs, _ = make_images(3, H, W, 123)
+    ts = torch.tensor([[H, W]])
+    kf = KeyframeFrontend(cuda_model)
+    for b in range(3):
+        kf.add_view(imgs[b:b + 1].cuda(), ts)
+    i, js = 2, [1, 0]
+    res = kf.regress_views(i, js)
+    orc = StaOracle(state_dict, emulate_bf16=True)
+    pos = token_positions(1, H // 16, W // 16)
+    for e, j in enumerate(js):
+        fi, fj = kf.enc_features[i].cpu(), kf.enc_features[j].cpu()
+        with torch.no_grad():
+            d_ij, d_ji = orc.decode_stereo(fi, fj, pos, pos)
+            pose = orc.head_pose(d_ij[-1][:, 0, :])
+            r_ij = orc.head_pts([fi] + [t[:, 1:, :] for t in d_ij], H, W)
+            r_ji = orc.head_pts([fj] + [t[:, 1:, :] for t in d_ji], H, W)
+        assert maxn(res["pose"][e:e + 1], pose["pose"]) < TOL_EMU["relative_pose"]
+        assert maxn(res["pose_conf"][e:e + 1], pose["conf"]) < TOL_EMU["relative_pose_conf"]
+        assert maxn(res["pts3d"][0, e:e + 1], r_ij["pts3d"]) < TOL_EMU["pts3d_pred"]
+        assert maxn(res["pts3d"][1, e:e + 1], r_ji["pts3d"]) < TOL_EMU["pts3d_pred"]
+        assert maxn(res["conf"][0, e:e + 1], r_ij["conf"]) < TOL_EMU["conf"]
+        assert maxn(res["conf"][1, e:e + 1], r_ji["conf"]) < TOL_EMU["conf"]
+        pcls = torch.cat([r_ij["pts3d"], r_ji["pts3d"]], dim=0).numpy()
+        confs = torch.cat([r_ij["conf"], r_ji["conf"]], dim=0).numpy()
+        K_ref = orc_intri(pcls, confs)
+        assert np.allclose(res["intri"][e].cpu().numpy(), K_ref, rtol=5e-2), (res["intri"][e], K_ref)
+
+
+def orc_intri(pcls, confs):
+    return orc.estimate_intrinsic_from_pts3d(pcls, confs, True)
+
+
+def test_gated_keyframe_step_keeps_the_reference_early_out(cuda_model):
+    """slam.py:169-170: an edge with rel_pose_conf < thres that is not the immediate neighbour (i - j != 1) is rejected
+    BEFORE the DPT heads.  The gated batched step must (a) return None for exactly those edges, (b) give the kept edges
+    the same results as the ungated batch, with one host synchronisation for the whole keyframe."""
+    from vista_slam_b200.keyframe import KeyframeFrontend
+    H, W = 64, 80
+    imgs, _ = make_images(5, H, W, 321)
+    ts = torch.tensor([[H, W]])
+    kf = KeyframeFrontend(cuda_model)
+    for b in range(5):
+        kf.add_view(imgs[b:b + 1].cuda(), ts)
+    i, js = 4, [3, 2, 1, 0]
+    full = kf.regress_views(i, js)
+    confs = full["pose_conf"].cpu()
+    # threshold between the candidates' confidences: rejects some non-neighbour edges, keeps others
+    order = sorted(float(c) for c in confs[1:])
+    thres = 0.5 * (order[0] + order[1]) if order[0] != order[1] else order[0] + 1e-6
+    out = kf.regress_views_gated(i, js, thres)
+    assert len(out) == 4
+    n_rej = 0
+    for e, j in enumerate(js):
+        pose, pconf, cf, intri, depths = out[e]
+        assert torch.equal(pose[0], full["pose"][e]) and torch.equal(pconf[0], full["pose_conf"][e])
+        rejected = float(confs[e]) < thres and i - j != 1
+        if rejected:
+            n_rej += 1
+            assert cf is None and intri is None and depths is None
+        else:
+            # same kernels on the same decoder hooks; only the DPT batch composition differs
+            assert maxn(cf, full["conf"][:, e]) < 2e-2
+            assert maxn(depths, full["depths"][:, e]) < 2e-2
+            assert maxn(intri, full["intri"][e]) < 2e-2
+    assert 1 <= n_rej <= 2
+    # everything rejected except the immediate neighbour (which the reference always keeps)
+    out = kf.regress_views_gated(i, js, 2.0)
+    assert out[0][2] is not None and all(o[2] is None for o in out[1:])
+    # nothing rejected == the ungated batch, bit for bit (same tile routes)
+    out = kf.regress_views_gated(i, js, -1.0)
+    for e in range(4):
+        assert torch.equal(out[e][2], full["conf"][:, e]) and torch.equal(out[e][4], full["depths"][:, e])

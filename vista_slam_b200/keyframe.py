@@ -66,6 +66,55 @@ class KeyframeFrontend:
                 "conf": conf, "intri": intri, "depths": depth, "conf_mean": cmean}
 
     @torch.no_grad()
+    def regress_views_gated(self, i, js, rel_pose_thres):
+        """The keyframe step with the reference's early-out (slam.py:169-170) kept: ONE decoder + pose-head pass over all
+        candidate edges (i, j), ONE device-to-host copy of the K pose confidences, then the DPT heads and the pointmap
+        consumers only for the edges the reference would keep (`conf >= thres or i - j == 1`).
+
+        Returns a list with one entry per candidate, in the return convention of OnlineSLAM.regress_two_views
+        (slam.py:153-189) minus the pypose conversion, which stays with the caller:
+            (pose_ij [1,4,4], rel_pose_conf_ij [1], confs [2,H,W] | None, intri [3,3] | None, depths [2,H,W] | None)
+        -- the last three are None for rejected edges, exactly where the reference returns None."""
+        import ctypes
+        js = list(js)
+        K = len(js)
+        if K == 0:
+            return []
+        H, W = self.img_shapes[i]
+        if any(self.img_shapes[j] != (H, W) for j in js):
+            raise ValueError("all views of a batch must have the same size")
+        m = self.frontend
+        fi = self.enc_features[i].expand(K, -1, -1).contiguous() if K > 1 else self.enc_features[i]
+        fj = torch.cat([self.enc_features[j] for j in js], dim=0) if K > 1 else self.enc_features[js[0]]
+        L = m._ready(fi)
+        dev = fi.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        pose = torch.empty(2, K, 4, 4, **f32)
+        pconf = torch.empty(2, K, **f32)
+        with torch.cuda.device(dev):
+            _lib.check(L.sta_regress_pairs_begin(m._handle, _lib.ptr(fi), _lib.ptr(fj), K, H, W, _lib.ptr(pose), _lib.ptr(pconf),
+                                                 _lib.cur_stream()), "sta_regress_pairs_begin")
+            conf_host = pconf[0].cpu()  # the one host synchronisation of the keyframe (slam.py:169 has one per edge)
+            keep = [k for k, j in enumerate(js) if not (float(conf_host[k]) < rel_pose_thres and i - j != 1)]
+            n = len(keep)
+            out = [(pose[0, k:k + 1], pconf[0, k:k + 1], None, None, None) for k in range(K)]
+            if n == 0:
+                return out
+            pts = torch.empty(2, n, H, W, 3, **f32)
+            conf = torch.empty(2, n, H, W, **f32)
+            intri = torch.empty(n, 3, 3, **f32)
+            depth = torch.empty(2, n, H, W, **f32)
+            idx = (ctypes.c_int * n)(*keep)
+            _lib.check(L.sta_regress_pairs_finish(m._handle, idx, n, _lib.ptr(pts), _lib.ptr(conf), _lib.ptr(intri),
+                                                  _lib.ptr(depth), None, _lib.ptr(_scratch_for(dev, 2 * n)), _lib.cur_stream()),
+                       "sta_regress_pairs_finish")
+        for pos, k in enumerate(keep):
+            out[k] = (pose[0, k:k + 1], pconf[0, k:k + 1], conf[:, pos], intri[pos], depth[:, pos])
+        self.last_pts3d = pts  # [2, n, H, W, 3] of the kept edges (diagnostics / tests)
+        self.last_kept = keep
+        return out
+
+    @torch.no_grad()
     def regress_two_views(self, i, j):
         """K = 1 with the return convention of slam.py:153-189 minus the pypose conversion:
         (pose_ij [1,4,4], rel_pose_conf_ij [1], confs [2,H,W], intri [3,3], depths [2,H,W])."""

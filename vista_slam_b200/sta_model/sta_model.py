@@ -197,6 +197,7 @@ class SymmetricTwoViewAssociation(nn.Module):
     def load_state_dict(self, ckpt, **kw):  # sta_model.py:143-144
         out = super().load_state_dict(ckpt, **kw)
         self._uploaded_key = None
+        self._weights_external = False  # an explicit checkpoint replaces broadcast weights
         return out
 
     def set_freeze(self, freeze):  # sta_model.py:148-161
@@ -234,6 +235,11 @@ class SymmetricTwoViewAssociation(nn.Module):
         key = (like.device.index, self._state_key())
         if self._handle is not None and self._uploaded_key == key:
             return L
+        if getattr(self, "_weights_external", False) and self._handle is not None:
+            if self._uploaded_key is not None and self._uploaded_key[0] != like.device.index:
+                raise RuntimeError("this replica's weights were broadcast to cuda:%s; it cannot run on cuda:%s"
+                                   % (self._uploaded_key[0], like.device.index))
+            return L  # broadcast weights: the local parameters are placeholders and must not overwrite the arena
         with torch.cuda.device(like.device):
             if self._handle is None:
                 self._handle = self._create(L)
@@ -273,6 +279,8 @@ class SymmetricTwoViewAssociation(nn.Module):
         afterwards).  Non-source ranks need no state dict."""
         import torch.distributed as dist
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if device.index is None:  # 'cuda' -> the concrete ordinal, so that _ready() computes the same key later
+            device = torch.device("cuda", torch.cuda.current_device())
         probe = torch.empty(1, device=device)
         L = _lib.lib()
         if dist.get_rank(group) == src:
@@ -288,6 +296,8 @@ class SymmetricTwoViewAssociation(nn.Module):
         if dist.get_rank(group) != src:
             _lib.check(L.sta_mark_all_loaded(self._handle), "sta_mark_all_loaded")
             self._uploaded_key = (device.index, self._state_key())
+            # the arena now holds rank `src`'s weights, NOT this module's (random-init) parameters: never re-upload
+            self._weights_external = True
 
     # ------------------------------------------------------------------ reference API: compute
     @torch.no_grad()
@@ -378,8 +388,10 @@ class SymmetricTwoViewAssociation(nn.Module):
             return self._dpt(decout, H, W)
         if bool((~is_landscape).all()):
             return {k: v.swapaxes(1, 2) for k, v in self._dpt(decout, W, H).items()}
-        res_l = self._dpt([d[is_landscape] for d in decout], H, W)
-        res_p = {k: v.swapaxes(1, 2) for k, v in self._dpt([d[~is_landscape] for d in decout], W, H).items()}
+        # only the hooked layers are read (heads/dpt_head.py:112); forward() passes None for the others
+        res_l = self._dpt([None if d is None else d[is_landscape] for d in decout], H, W)
+        res_p = {k: v.swapaxes(1, 2)
+                 for k, v in self._dpt([None if d is None else d[~is_landscape] for d in decout], W, H).items()}
         out = {}
         for k in res_l:
             x = res_l[k].new_empty((len(ts),) + tuple(res_l[k].shape[1:]))
@@ -408,13 +420,18 @@ class SymmetricTwoViewAssociation(nn.Module):
             _lib.check(L.sta_forward_pairs(self._handle, _lib.ptr(img1), _lib.ptr(img2), int(img1.dtype == torch.bfloat16),
                                            B, H, W, _lib.ptr(pts), _lib.ptr(conf), _lib.ptr(pose), _lib.ptr(pconf),
                                            _lib.cur_stream()), "sta_forward_pairs")
+        if self.landscape_only and H > W:
+            # all-portrait batch: the reference's head wrapper returns the maps transposed to landscape
+            # (transpose_to_landscape, utils/misc.py:48-61) -- same here, as a view
+            pts, conf = pts.swapaxes(2, 3), conf.swapaxes(2, 3)
         return tuple({"pts3d_pred": pts[v], "conf": conf[v], "relative_pose": pose[v], "relative_pose_conf": pconf[v]}
                      for v in range(2))
 
     @torch.no_grad()
     def forward_pairs_host(self, img1, img2, out=None):
         """End-to-end variant with HOST tensors (pinned recommended): H2D copies, forward, D2H copies and a
-        stream synchronise all happen inside the C call (sta_forward_pairs_host)."""
+        stream synchronise all happen inside the C call (sta_forward_pairs_host).  The maps come back in the image's own
+        (H, W) orientation: no landscape transposition is applied to the caller's buffers."""
         if img1.is_cuda or img2.is_cuda:
             raise ValueError("forward_pairs_host takes host tensors")
         L = self._ready(torch.empty(1, device="cuda"))
