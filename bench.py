@@ -34,8 +34,18 @@ METRIC = "sta_image_pairs_per_sec"
 UNIT = "pairs/s"
 
 
-def make_config(P, world, H, W):
+def make_config(P, world, H, W, total=None):
     from vista_slam_b200.flops import flops_per_pair
+    if total is not None:  # cfg-5: a fixed global batch split contiguously over the ranks (strong scaling)
+        from vista_slam_b200.dist import pair_shard
+        shards = [pair_shard(total, r, world) for r in range(world)]
+        return {"workload": "cfg-5: %d synthetic %dx%d bf16 pairs per step in total, contiguous B/R shard per rank (%s pairs), "
+                            "STA forward only, random-init weights" % (total, W, H, "/".join(str(b - a) for a, b in shards)),
+                "pairs_per_gpu": max(b - a for a, b in shards), "global_pairs": total, "height": H, "width": W,
+                "parallelism": "contiguous pair shard per rank (vista_slam_b200/dist.py::pair_shard), 1 NCCL weight broadcast, "
+                               "no data-path collective",
+                "l2_policy": "no explicit flush: weights (0.88 GB) + activations exceed the 126 MB L2",
+                "gflop_per_pair": flops_per_pair(H, W) / 1e9}
     return {"workload": "cfg-2: %d synthetic %dx%d bf16 pairs per GPU per step, STA forward only "
                         "(2 enc + symmetric dec + 2 DPT + 2 pose heads per pair), random-init weights" % (P, W, H),
             "pairs_per_gpu": P, "global_pairs": P * world, "height": H, "width": W,
@@ -219,6 +229,13 @@ def run_b200_arm(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     H, W, P = args.height, args.width, args.pairs
+    total = args.total_pairs
+    if total is not None:  # cfg-5 strong scaling: this rank's contiguous block of the global batch
+        from vista_slam_b200.dist import pair_shard
+        lo, hi = pair_shard(total, rank, world)
+        P = hi - lo
+        if P == 0:
+            raise SystemExit("--total-pairs %d leaves rank %d without work" % (total, rank))
     model = STA()  # random-init weights of the reference architecture (no network for the checkpoint)
     model.eval()
     if world > 1:
@@ -260,7 +277,8 @@ def run_b200_arm(args, rank, local_rank, world):
     launches = model.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
-    value = world * P / (ms_step / 1e3)
+    global_pairs = total if total is not None else world * P
+    value = global_pairs / (ms_step / 1e3)
     ok = bool(torch.isfinite(out[0]["pts3d_pred"]).all()) and bool(torch.isfinite(out[1]["relative_pose"]).all())
 
     # ---------------- end-to-end through the host-buffer C-ABI call (`e2e`) ----------------
@@ -276,7 +294,7 @@ def run_b200_arm(args, rank, local_rank, world):
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)) / args.steps
-    e2e_value = world * P / (e2e_ms / 1e3)
+    e2e_value = global_pairs / (e2e_ms / 1e3)
     h2d = 2 * h1.numel() * h1.element_size()
     d2h = sum(t.numel() * t.element_size() for t in hout.values())
 
@@ -312,8 +330,9 @@ def run_b200_arm(args, rank, local_rank, world):
         "family_ms_per_step": {"gemm_linear": ms4[0] / prof_steps, "gemm_conv3x3": ms4[1] / prof_steps,
                                "attention": ms4[2] / prof_steps, "layernorm": ms4[3] / prof_steps},
         "attention_tflops": P * attn_flops_pair / (ms4[2] / prof_steps / 1e3) / 1e12 if ms4[2] > 0 else None,
-        "whole_step_tflops": value * flop_pair / 1e12 / world,
-        "whole_step_frac": value * flop_pair / 1e12 / world / peak,
+        # rank 0's own work over the max-over-ranks time
+        "whole_step_tflops": P * flop_pair / (ms_step / 1e3) / 1e12,
+        "whole_step_frac": P * flop_pair / (ms_step / 1e3) / 1e12 / peak,
     }
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
@@ -325,9 +344,9 @@ def run_b200_arm(args, rank, local_rank, world):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "impl": "b200",
-            "config": make_config(P, world, H, W),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if total is not None else "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "b200",
+            "config": make_config(P, world, H, W, total),
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                                       "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                                       # copy time not hidden behind the kernels (H2D of the first chunk, D2H tail)
@@ -348,6 +367,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=16, help="pairs per GPU per step (cfg-2: 16)")
     ap.add_argument("--height", type=int, default=384)
     ap.add_argument("--width", type=int, default=512)
+    ap.add_argument("--total-pairs", type=int, default=None,
+                    help="cfg-5: global batch split contiguously over the ranks (strong scaling); overrides --pairs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -216,6 +216,21 @@ int sta_depth_scale(const float* Di, const float* Dj, const float* ci, const flo
                     void* scratch, void* stream);
 
 
+/* ---- Sim(3) pose-graph Levenberg-Marquardt step: one iteration of the optimisation in
+ * OnlineSLAM.pose_graph_optimize (vista_slam/slam.py:108-140) over PoseGraphOpt (vista_slam/pose_graph.py:70-154):
+ * residuals r_e = Log(T_e X_i^-1 X_j) of the edges with at least one optimised endpoint, their Jacobians w.r.t. left
+ * perturbations X <- Exp(delta) X (what PyPose's LieTensor parameters use), A = J^T W J with W = diag(weights_e) and the LM
+ * damping of pp.optim.LM.step (diagonal clamped to [dmin, dmax], then scaled by 1 + damping), a dense Cholesky solve of
+ * A d = -J^T W r, and the update.  Device pointers: nodes / nodes_out [num_nodes][8] and meas [num_edges][8] fp32 Sim3 in
+ * PyPose's layout (tx ty tz | qx qy qz qw | s), edges [num_edges][2] int64 (i, j), weights [num_edges][7] fp32,
+ * opt_idx [num_opt] int64 (the optimised nodes, all others stay fixed).  info_out (device) [4] fp64 = {loss before,
+ * loss after, |delta|_2, Cholesky ok (1/0)}; loss = sum r^T W r.  fp64 inside, deterministic, no host synchronisation: the
+ * caller reads info_out to accept or reject the step (as pp.optim.LM does).  scratch: sta_pose_graph_scratch_bytes. ---- */
+size_t sta_pose_graph_scratch_bytes(int num_nodes, int num_edges, int num_opt);
+int sta_pose_graph_lm_step(const float* nodes, int num_nodes, const int64_t* edges, const float* meas, const float* weights,
+                           int num_edges, const int64_t* opt_idx, int num_opt, double damping, double dmin, double dmax,
+                           float* nodes_out, double* info_out, void* scratch, void* stream);
+
 /* ---- image preprocessing: SLAM_image_only.process_image
  * (vista_slam/datasets/slam_images_only.py:22-34 -> datasets/base/base_view_graph_dataset.py:171-225 ->
  * utils/cropping.py:54-84,102-118 with PIL LANCZOS -> utils/image.py:13) on the device, bit-exact with PIL's 8-bit

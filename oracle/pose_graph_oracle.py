@@ -24,7 +24,7 @@ from scipy.linalg import expm
 
 # ---------------------------------------------------------------------------------------------- quaternions
 def quat_to_rot(q):
-    x, y, z, w = q
+    x, y, z, w = np.asarray(q, dtype=np.float64) / np.linalg.norm(q)  # fp32-rounded inputs are not exactly unit
     return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])

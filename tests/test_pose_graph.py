@@ -154,3 +154,57 @@ def test_lm_step_is_a_damped_gauss_newton_solve():
     Ad = A.copy()
     Ad[np.diag_indices_from(Ad)] *= 1.0 + 1e-4
     assert np.allclose(Ad @ delta, -g, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _to_torch(a, dtype=None):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return (t.to(dtype) if dtype is not None else t).cuda()
+
+
+@pytest.mark.gpu
+def test_gpu_lm_step_matches_the_oracle():
+    """one LM step on the device (fp64 inside, fp32 node tensors) vs the numpy oracle on the same fp32-rounded inputs:
+    losses, update norm and the updated nodes; windowed problem (fixed + optimised nodes, unrelated edges present)."""
+    import torch
+    from vista_slam_b200.pose_graph import PoseGraphOpt
+    rng = np.random.default_rng(6)
+    gt, init, edges, meas, weights = make_graph(rng, n_nodes=40, n_loops=10, noise=0.05, meas_noise=0.02)
+    init32, meas32, w32 = init.astype(np.float32), meas.astype(np.float32), weights.astype(np.float32)
+    for opt_idx in (list(range(1, 40)), list(range(25, 40))):
+        g = PoseGraphOpt(_to_torch(init32), torch.tensor(opt_idx))
+        cand, l0, l1, dn, ok = g.lm_step(_to_torch(edges), _to_torch(meas32), _to_torch(w32), 1e-4)
+        ref_nodes, r0, r1, delta = pg.lm_step(init32.astype(np.float64), edges, meas32.astype(np.float64), w32.astype(np.float64),
+                                              opt_idx, 1e-4)
+        assert ok
+        assert abs(l0 - r0) < 1e-8 * max(1.0, r0) and abs(l1 - r1) < 1e-6 * max(1.0, r0), (l0, r0, l1, r1)
+        assert abs(dn - np.linalg.norm(delta)) < 1e-8 * max(1.0, np.linalg.norm(delta))
+        got = cand.cpu().numpy().astype(np.float64)
+        for v in range(40):
+            assert np.allclose(pg.sim3_matrix(got[v]), pg.sim3_matrix(ref_nodes[v]), atol=2e-6), v   # fp32 output rounding
+        rel = g.get_related_edge_idxs(_to_torch(edges)).cpu().numpy()
+        assert np.array_equal(rel, pg.related_edges(edges, opt_idx))
+
+
+@pytest.mark.gpu
+def test_gpu_optimisation_recovers_a_planted_graph_and_is_deterministic():
+    import torch
+    from vista_slam_b200.pose_graph import PoseGraphOpt
+    rng = np.random.default_rng(7)
+    gt, init, edges, meas, weights = make_graph(rng, n_nodes=60, n_loops=15, noise=0.05)
+    opt_idx = torch.arange(1, 60)
+    args = (_to_torch(edges), _to_torch(meas, torch.float32), _to_torch(weights, torch.float32))
+    g = PoseGraphOpt(_to_torch(init, torch.float32), opt_idx)
+    losses = g.optimize(*args)
+    assert losses[-1] < 1e-9 and losses[0] > losses[-1]
+    got = g.get_nodes().cpu().numpy().astype(np.float64)
+    for v in range(60):
+        assert np.allclose(pg.sim3_matrix(got[v]), pg.sim3_matrix(gt[v]), atol=2e-4), v
+    g2 = PoseGraphOpt(_to_torch(init, torch.float32), opt_idx)
+    assert g2.optimize(*args) == losses and torch.equal(g2.get_nodes(), g.get_nodes())   # no atomics anywhere
+    # same iteration in the oracle: same loss trajectory
+    _, ref_losses = pg.optimize(init.astype(np.float32).astype(np.float64), edges, meas.astype(np.float32).astype(np.float64),
+                                weights.astype(np.float32).astype(np.float64), list(range(1, 60)))
+    assert len(ref_losses) == len(losses)
+    assert abs(ref_losses[0] - losses[0]) < 1e-5 * max(ref_losses[0], 1e-12) + 1e-9

@@ -9,7 +9,8 @@ import sys
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
-FEATS = [0, 1, 7, 11, 15, 31, 23]
+FEATS = [5, 13, 69, 77, 93]
+REF_LIB = os.path.join(ROOT, "tools", "ab", "libsta_r01attn.so")  # optional: a build with the round-1 attention kernel
 
 
 def child():
@@ -75,7 +76,13 @@ if __name__ == "__main__":
     else:
         feats = [int(a) for a in sys.argv[1:]] or FEATS
         for rep in range(2):
-            for f in feats:
-                env = dict(os.environ, STA_ATTN_FEAT=str(f), ATTN_AB_CHILD="1")
+            if os.path.exists(REF_LIB):
+                env = dict(os.environ, STA_B200_LIB=REF_LIB, ATTN_AB_CHILD="1", STA_ATTN_FEAT="r01")
                 r = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, capture_output=True, text=True, timeout=300)
-                print(r.stdout.strip() or ("feat %d FAILED: %s" % (f, r.stderr[-400:])), flush=True)
+                print(r.stdout.strip() or ("r01 lib FAILED: %s" % r.stderr[-400:]), flush=True)
+            for f in feats:
+                for pp in ("1", "0"):
+                    env = dict(os.environ, STA_ATTN_FEAT=str(f), ATTN_AB_CHILD="1", STA_ATTN_PINGPONG=pp)
+                    r = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, capture_output=True, text=True,
+                                       timeout=300)
+                    print(("pingpong %s " % pp) + (r.stdout.strip() or ("feat %d FAILED: %s" % (f, r.stderr[-400:]))), flush=True)

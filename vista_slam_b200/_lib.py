@@ -93,6 +93,10 @@ def lib():
     L.sta_pointmap_scratch_bytes.restype = ctypes.c_size_t
     L.sta_pointmap_consumers.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
     L.sta_depth_scale.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
+    L.sta_pose_graph_scratch_bytes.argtypes = [i, i, i]
+    L.sta_pose_graph_scratch_bytes.restype = ctypes.c_size_t
+    L.sta_pose_graph_lm_step.argtypes = [vp, i, vp, vp, vp, i, vp, i, ctypes.c_double, ctypes.c_double, ctypes.c_double, vp, vp,
+                                         vp, vp]
     _lib = L
     return L
 

@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libsta_b200.so")
-SOURCES = ["host_util.cu", "gemm.cu", "attention.cu", "kernels.cu", "pointmap.cu", "preprocess.cu", "runtime.cu"]
+SOURCES = ["host_util.cu", "gemm.cu", "attention.cu", "kernels.cu", "pointmap.cu", "preprocess.cu", "pose_graph.cu", "runtime.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-std=c++17", "-O3", "-lineinfo",

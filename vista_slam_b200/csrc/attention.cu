@@ -31,6 +31,8 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace sta {
 
 namespace {
@@ -54,11 +56,16 @@ constexpr float kScaleLog2Hd64 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5
 enum AttnFeat : int {
   AF_SKIP = 1,   // warps whose 32 query rows are all >= nq only keep the barrier protocol going (no TMEM loads, no math):
                  // the decoder's 769 = 6 x 128 + 1 rows then cost 6.25 instead of 8 tiles of softmax work
-  AF_MAX3 = 2,   // row maximum with 3-input FMNMX3
+  AF_MAX3 = 2,   // (unused: the compiler already fuses the fmaxf chains into 3-input FMNMX3)
   AF_IMM = 4,    // scale * log2(e) as an immediate operand of the FFMA (only when scale == 0.125)
   AF_ONES = 8,   // row sum l from the tensor core: one extra N = 16 MMA per key step multiplies P by a tile of ones, so
                  // l accumulates in TMEM next to O (and is the sum of exactly the bf16 P values that multiply V)
   AF_EMU = 16,   // 2 of every 8 exponentials on the FMA pipe (ex2_fma) instead of the 16-lane/clk MUFU
+  AF_2PASS = 64, // the score row is read from TMEM twice, 32 columns at a time (pass 1: row maximum, pass 2: exponentials),
+                 // instead of being held in 128 registers: ptxas allocates for the launch-bound cap (168 registers, it does
+                 // not widen for setmaxnreg.inc), so the one-pass exp2 loop is register-starved; the two-pass loops are
+                 // software-pipelined (TMEM load of chunk c+1 under the math of chunk c).  S is released together with P
+                 // (no s_free barrier): the MMA thread issues P_t V and then S_t(n+1) back to back.
 };
 
 struct AttnParams {
@@ -222,8 +229,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       uint32_t v_ph = 0;
       for (int n = 0; n < total; ++n) {
         const bool trc = trace_cta && n < 32;
-        // S_t(n+1) as soon as group t holds S_t(n) in registers
-        if (n + 1 < total) {
+        // S_t(n+1) as soon as group t holds S_t(n) in registers (2PASS: issued right after P_t(n) V instead, see below)
+        if (!(FEAT & AF_2PASS) && n + 1 < total) {
           for (int t = 0; t < 2; ++t) {
             if (trc) p.dbg[16 * n + 4 * t + 0] = clock64();
             mbar_wait(&s_free[t], n & 1);
@@ -244,16 +251,29 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint64_t pdesc1 = make_smem_desc_sw128(smem_u32(sP + t * 2 * TILE_BYTES + TILE_BYTES));
           const uint32_t d = tmem_base + 256 + t * 64;
           const uint32_t dl = tmem_base + 384 + t * 16;
-          const int ksteps = (narrow_tail && j == T - 1) ? 1 : 8;  // a narrow tail tile holds <= 16 keys
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
-            // V advances 16 keys = 16 rows x 128 B = 2048 B per step; first key tile of an item overwrites O
-            umma_bf16(d, pd, vdesc + (2048 >> 4) * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-            // row sums: l_t (+)= P_t(n) 1  (all 16 columns equal; the ones tile is the same for every key step)
-            if constexpr (FEAT & AF_ONES) umma_bf16(dl, pd, ones_desc, idesc_s16, (j > 0 || k > 0) ? 1u : 0u);
+          // V advances 16 keys = 16 rows x 128 B = 2048 B per step; the first key tile of an item overwrites O.
+          // Row sums (AF_ONES): l_t (+)= P_t(n) 1 -- all 16 columns equal; the ones tile is the same for every key step.
+          const uint32_t acc0 = j > 0 ? 1u : 0u;
+          if (narrow_tail && j == T - 1) {  // a narrow tail tile holds <= 16 keys: one step
+            umma_bf16(d, pdesc0, vdesc, idesc_o, acc0);
+            if constexpr (FEAT & AF_ONES) umma_bf16(dl, pdesc0, ones_desc, idesc_s16, acc0);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
+              umma_bf16(d, pd, vdesc + (2048 >> 4) * k, idesc_o, k > 0 ? 1u : acc0);
+            }
+            if constexpr (FEAT & AF_ONES) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                umma_bf16(dl, (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3), ones_desc, idesc_s16, k > 0 ? 1u : acc0);
+            }
           }
           if (t == 1) umma_commit(&v_empty[v_st]);
           umma_commit(&o_full[t]);
+          if constexpr (FEAT & AF_2PASS) {
+            if (n + 1 < total) issue_s(t);  // group t finished reading S_t(n) before it signalled p_full
+          }
           if (trc) p.dbg[16 * n + 8 + 4 * t + 2] = clock64();
         }
         if (++v_st == KV_STAGES) { v_st = 0; v_ph ^= 1; }
@@ -305,98 +325,213 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tmem_st_wait();
     };
 
+    // P = exp2(S*c - m) for NCH 16-byte chunks of 8 keys -> bf16, 128B-swizzled K-major tile; returns the row sum
+    auto exp_store = [&](const uint32_t* s, float m_used, auto nch_tag, int chunk0 = 0) -> float {
+      constexpr int NCH = decltype(nch_tag)::value;
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x = fmaf(__uint_as_float(s[8 * c + i]), scale_log2, -m_used);
+          if ((FEAT & AF_EMU) && (i == 3 || i == 7)) e[i] = ex2_fma(x);
+          else e[i] = ex2_approx(x);
+        }
+        if constexpr (!(FEAT & AF_ONES)) {
+          rs0 += e[0] + e[4];
+          rs1 += e[1] + e[5];
+          rs2 += e[2] + e[6];
+          rs3 += e[3] + e[7];
+        }
+        uint4 q;
+        q.x = pack_bf16x2(e[0], e[1]);
+        q.y = pack_bf16x2(e[2], e[3]);
+        q.z = pack_bf16x2(e[4], e[5]);
+        q.w = pack_bf16x2(e[6], e[7]);
+        const int cc = chunk0 + c;
+        *reinterpret_cast<uint4*>(prow + (cc >> 3) * TILE_BYTES + (((cc & 7) ^ rx) << 4)) = q;
+      }
+      return (rs0 + rs1) + (rs2 + rs3);
+    };
+
     for (int it = 0; it < my_items; ++it) {
       int q0, head, b, kvb;
       decode(static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x), q0, head, b, kvb);
+      // AF_SKIP: all 32 rows of this warp lie beyond nq (ragged last query tile, or a dead second tile): the warp only
+      // keeps the barrier protocol in step -- the same waits and arrivals as a live warp, in the same order, but no TMEM
+      // traffic and no math.  Its P rows keep stale values: rows of O are independent and rows >= nq are never stored.
+      if ((FEAT & AF_SKIP) && (q0 + grp * 128 + quarter * 32 >= p.nq)) {
+        for (int j = 0; j < T; ++j, ++n) {
+          mbar_wait(&s_full[grp], n & 1);
+          tc_fence_before();
+          __syncwarp();
+          if (!(FEAT & AF_2PASS) && lane == 0) mbar_arrive(&s_free[grp]);
+          if (j > 0) mbar_wait(&o_full[grp], (n - 1) & 1);
+          if (j == 0 && it > 0) named_bar_sync(1 + grp, 128);
+          turn_wait();
+          turn_pass();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[grp]);
+        }
+        mbar_wait(&o_full[grp], (n - 1) & 1);
+        named_bar_sync(1 + grp, 128);
+        continue;
+      }
       float m_used = -INFINITY;  // maximum the exponentials of this row are currently relative to (log2 domain)
       float l = 0.f;
-      // AF_SKIP: all 32 rows of this warp lie beyond nq (ragged last query tile, or a dead second tile): the warp only
-      // keeps the barrier protocol in step -- same waits and arrivals as a live warp, no TMEM traffic, no math.  Its P
-      // rows keep stale (finite or not) values: rows of O are independent and rows >= nq are never stored.
-      const bool dead = (FEAT & AF_SKIP) && (q0 + grp * 128 + quarter * 32 >= p.nq);
 
       for (int j = 0; j < T; ++j, ++n) {
         const bool trc = trace_thr && n < 30;
         const int nvalid = p.nk - j * 128;  // >= 1
-        const bool narrow = nvalid <= 16 && j == T - 1;
         if (trc) p.dbg[512 + grp * 256 + 8 * n + 0] = clock64();
         mbar_wait(&s_full[grp], n & 1);
         tc_fence_after();
         if (trc) p.dbg[512 + grp * 256 + 8 * n + 1] = clock64();
+        if (nvalid <= 16 && j == T - 1) {
+          // ---- narrow tail tile: S is 128 x 16, P V uses a single 16-key step ----
+          uint32_t s16[16];
+          tmem_ld16(tS, s16);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (!(FEAT & AF_2PASS) && lane == 0) mbar_arrive(&s_free[grp]);
+          float mxn = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (i >= nvalid) s16[i] = 0xff800000u;
+            mxn = fmaxf(mxn, __uint_as_float(s16[i]));
+          }
+          const float m_true = mxn * scale_log2;
+          const bool raise = m_true > m_used + kRescaleThreshold;
+          const float m_new = raise ? m_true : m_used;
+          const float factor = raise ? ex2_approx(m_used - m_new) : 1.0f;
+          l *= factor;
+          m_used = m_new;
+          if (j > 0) {
+            mbar_wait(&o_full[grp], (n - 1) & 1);
+            if (__any_sync(0xffffffffu, raise)) rescale_acc(factor);
+          }
+          if (j == 0 && it > 0) {
+            if (warp == 4 + 4 * grp && lane == 0) tma_store_wait_read();
+            named_bar_sync(1 + grp, 128);
+          }
+          turn_wait();
+          l += exp_store(s16, m_used, std::integral_constant<int, 2>{});
+          turn_pass();
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[grp]);
+          continue;
+        }
+        if constexpr (FEAT & AF_2PASS) {
+          // ---- pass 1: row maximum, 32 columns at a time; the load of chunk c+1 is in flight under the maxima of chunk c ----
+          uint32_t buf[2][32];
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+          tmem_ld32(tS, buf[0]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            tmem_ld_wait();
+            if (c < 3) tmem_ld32(tS + 32 * (c + 1), buf[(c + 1) & 1]);
+            uint32_t* v = buf[c & 1];
+            if (nvalid < 128) {  // ragged last key tile
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (32 * c + i >= nvalid) v[i] = 0xff800000u;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+              mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+              mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
+              mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
+            }
+          }
+          if (trc) p.dbg[512 + grp * 256 + 8 * n + 2] = clock64();
+          const float m_true = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+          const bool raise = m_true > m_used + kRescaleThreshold;  // always true on the first tile (m_used = -inf)
+          const float m_new = raise ? m_true : m_used;
+          const float factor = raise ? ex2_approx(m_used - m_new) : 1.0f;
+          l *= factor;
+          m_used = m_new;
+          if (trc) p.dbg[512 + grp * 256 + 8 * n + 3] = clock64();
+          if (j > 0) {
+            mbar_wait(&o_full[grp], (n - 1) & 1);
+            if (__any_sync(0xffffffffu, raise)) rescale_acc(factor);
+          }
+          if (j == 0 && it > 0) {
+            if (warp == 4 + 4 * grp && lane == 0) tma_store_wait_read();
+            named_bar_sync(1 + grp, 128);
+          }
+          if (trc) p.dbg[512 + grp * 256 + 8 * n + 4] = clock64();
+          turn_wait();
+          // ---- pass 2: exponentials, again 32 columns at a time with the next chunk's load in flight ----
+          tc_fence_after();
+          tmem_ld32(tS, buf[0]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            tmem_ld_wait();
+            if (c < 3) tmem_ld32(tS + 32 * (c + 1), buf[(c + 1) & 1]);
+            uint32_t* v = buf[c & 1];
+            if (nvalid < 128) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (32 * c + i >= nvalid) v[i] = 0xff800000u;
+            }
+            l += exp_store(v, m_used, std::integral_constant<int, 4>{}, 4 * c);
+          }
+          turn_pass();
+          fence_proxy_async_smem();
+          tc_fence_before();  // orders this thread's TMEM loads of S (and the O rescale) before the MMAs that follow p_full
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[grp]);
+          if (trc) p.dbg[512 + grp * 256 + 8 * n + 5] = clock64();
+          continue;
+        }
         // ---- the whole score row into registers; release the S buffer for the next Q K^T ----
         uint32_t s[128];
-        if (!dead) {
-          if (narrow) {
-            uint32_t (&s0)[16] = *reinterpret_cast<uint32_t(*)[16]>(&s[0]);
-            tmem_ld16(tS, s0);
-          } else {
-            uint32_t (&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
-            uint32_t (&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-            uint32_t (&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
-            uint32_t (&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
-            tmem_ld32(tS, s0);
-            tmem_ld32(tS + 32, s1);
-            tmem_ld32(tS + 64, s2);
-            tmem_ld32(tS + 96, s3);
-          }
+        {
+          uint32_t (&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+          uint32_t (&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+          uint32_t (&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+          uint32_t (&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+          tmem_ld32(tS, s0);
+          tmem_ld32(tS + 32, s1);
+          tmem_ld32(tS + 64, s2);
+          tmem_ld32(tS + 96, s3);
           tmem_ld_wait();
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[grp]);
         if (trc) p.dbg[512 + grp * 256 + 8 * n + 2] = clock64();
-        bool raise = false;
-        float factor = 1.0f;
-        if (!dead) {
-          float m_true;
-          if (narrow) {
-            // ---- narrow tail tile: S is 128 x 16, P V uses a single 16-key step ----
-            float mxn = -INFINITY;
+        if (nvalid < 128) {  // ragged last key tile: masked scores contribute exp2(-inf) = 0
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (i >= nvalid) s[i] = 0xff800000u;
-              mxn = fmaxf(mxn, __uint_as_float(s[i]));
-            }
-            m_true = mxn * scale_log2;
-          } else {
-            if (nvalid < 128) {  // ragged last key tile: masked scores contribute exp2(-inf) = 0
-#pragma unroll
-              for (int i = 0; i < 128; ++i)
-                if (i >= nvalid) s[i] = 0xff800000u;
-            }
-            // ---- row maximum (4 independent chains) ----
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-            if constexpr (FEAT & AF_MAX3) {
-#pragma unroll
-              for (int i = 0; i < 128; i += 8) {
-                mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-                mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-                mx2 = fmax3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-                mx3 = fmax3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 128; i += 4) {
-                mx0 = fmaxf(mx0, __uint_as_float(s[i]));
-                mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
-                mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
-                mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
-              }
-            }
-            m_true = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
-          }
-          // lazy rescaling: keep the old reference maximum unless the row maximum grew by more than 2^8
-          raise = m_true > m_used + kRescaleThreshold;  // always true on the first tile (m_used = -inf)
-          const float m_new = raise ? m_true : m_used;
-          factor = raise ? ex2_approx(m_used - m_new) : 1.0f;  // first tile: exp2(-inf) = 0
-          l *= factor;
-          m_used = m_new;
+          for (int i = 0; i < 128; ++i)
+            if (i >= nvalid) s[i] = 0xff800000u;
         }
+        // ---- row maximum (4 independent chains; the compiler fuses pairs into FMNMX3) ----
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+        }
+        const float m_true = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+        // lazy rescaling: keep the old reference maximum unless the row maximum grew by more than 2^8
+        const bool raise = m_true > m_used + kRescaleThreshold;  // always true on the first tile (m_used = -inf)
+        const float m_new = raise ? m_true : m_used;
+        const float factor = raise ? ex2_approx(m_used - m_new) : 1.0f;  // first tile: exp2(-inf) = 0
+        l *= factor;
+        m_used = m_new;
         if (trc) p.dbg[512 + grp * 256 + 8 * n + 3] = clock64();
         // the previous P V of this group must be complete before P is overwritten (and before O is rescaled)
         if (j > 0) {
           mbar_wait(&o_full[grp], (n - 1) & 1);
-          if (!dead && __any_sync(0xffffffffu, raise)) rescale_acc(factor);
+          if (__any_sync(0xffffffffu, raise)) rescale_acc(factor);
         }
         if (j == 0 && it > 0) {
           // the previous item's output tile was staged in this P buffer: its TMA store must have read it
@@ -404,37 +539,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           named_bar_sync(1 + grp, 128);
         }
         if (trc) p.dbg[512 + grp * 256 + 8 * n + 4] = clock64();
-        // ---- P = exp2(S*c - m_used) -> bf16, 128B-swizzled K-major tile in this group's P buffer ----
         turn_wait();
-        if (!dead) {
-          float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-          const int nchunk = narrow ? 2 : 16;  // 16-byte chunks of 8 keys
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            if (c < nchunk) {
-              float e[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float x = fmaf(__uint_as_float(s[8 * c + i]), scale_log2, -m_used);
-                if ((FEAT & AF_EMU) && (i == 3 || i == 7)) e[i] = ex2_fma(x);
-                else e[i] = ex2_approx(x);
-              }
-              if constexpr (!(FEAT & AF_ONES)) {
-                rs0 += e[0] + e[4];
-                rs1 += e[1] + e[5];
-                rs2 += e[2] + e[6];
-                rs3 += e[3] + e[7];
-              }
-              uint4 q;
-              q.x = pack_bf16x2(e[0], e[1]);
-              q.y = pack_bf16x2(e[2], e[3]);
-              q.z = pack_bf16x2(e[4], e[5]);
-              q.w = pack_bf16x2(e[6], e[7]);
-              *reinterpret_cast<uint4*>(prow + (c >> 3) * TILE_BYTES + (((c & 7) ^ rx) << 4)) = q;
-            }
-          }
-          if constexpr (!(FEAT & AF_ONES)) l += (rs0 + rs1) + (rs2 + rs3);
-        }
+        l += exp_store(s, m_used, std::integral_constant<int, 16>{});
         turn_pass();
         fence_proxy_async_smem();
         tc_fence_before();
@@ -448,26 +554,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_wait(&o_full[grp], (n - 1) & 1);
       tc_fence_after();
       if (trce) p.dbg[1100 + grp * 32 + it * 4 + 1] = clock64();
-      if (!dead) {
-        if constexpr (FEAT & AF_ONES) {
-          l = __uint_as_float(tmem_ld1(tL));
-          tmem_ld_wait();
-        }
-        const float inv_l = 1.0f / l;
+      if constexpr (FEAT & AF_ONES) {
+        l = __uint_as_float(tmem_ld1(tL));
+        tmem_ld_wait();
+      }
+      const float inv_l = 1.0f / l;
 #pragma unroll
-        for (int c = 0; c < 64; c += 32) {
-          uint32_t o[32];
-          tmem_ld32(tO + c, o);
-          tmem_ld_wait();
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t o[32];
+        tmem_ld32(tO + c, o);
+        tmem_ld_wait();
 #pragma unroll
-          for (int jc = 0; jc < 4; ++jc) {
-            uint4 q;
-            q.x = pack_bf16x2(__uint_as_float(o[8 * jc + 0]) * inv_l, __uint_as_float(o[8 * jc + 1]) * inv_l);
-            q.y = pack_bf16x2(__uint_as_float(o[8 * jc + 2]) * inv_l, __uint_as_float(o[8 * jc + 3]) * inv_l);
-            q.z = pack_bf16x2(__uint_as_float(o[8 * jc + 4]) * inv_l, __uint_as_float(o[8 * jc + 5]) * inv_l);
-            q.w = pack_bf16x2(__uint_as_float(o[8 * jc + 6]) * inv_l, __uint_as_float(o[8 * jc + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(prow + ((((c >> 3) + jc) ^ rx) << 4)) = q;
-          }
+        for (int jc = 0; jc < 4; ++jc) {
+          uint4 q;
+          q.x = pack_bf16x2(__uint_as_float(o[8 * jc + 0]) * inv_l, __uint_as_float(o[8 * jc + 1]) * inv_l);
+          q.y = pack_bf16x2(__uint_as_float(o[8 * jc + 2]) * inv_l, __uint_as_float(o[8 * jc + 3]) * inv_l);
+          q.z = pack_bf16x2(__uint_as_float(o[8 * jc + 4]) * inv_l, __uint_as_float(o[8 * jc + 5]) * inv_l);
+          q.w = pack_bf16x2(__uint_as_float(o[8 * jc + 6]) * inv_l, __uint_as_float(o[8 * jc + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(prow + ((((c >> 3) + jc) ^ rx) << 4)) = q;
         }
       }
       tc_fence_before();  // the next item's first P V overwrites O only after p_full, i.e. after these loads
@@ -725,7 +829,7 @@ int make_qkv_map(CUtensorMap* m, const bf16* base, long long ld, int ntok, int b
 }  // namespace
 
 // default feature set (updated from the A/B measurements in profiles/)
-constexpr int kDefaultFeat = AF_SKIP | AF_MAX3 | AF_IMM | AF_ONES;
+constexpr int kDefaultFeat = AF_SKIP | AF_IMM | AF_ONES;
 
 int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   STA_REQUIRE(a.batch > 0 && a.heads > 0 && a.nq > 0 && a.nk > 0, "empty attention problem");
@@ -798,11 +902,13 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   }
   STA_ATTN_CASE(0)
   STA_ATTN_CASE(AF_SKIP)
-  STA_ATTN_CASE(AF_SKIP | AF_MAX3 | AF_IMM)
-  STA_ATTN_CASE(AF_SKIP | AF_MAX3 | AF_ONES)
-  STA_ATTN_CASE(AF_SKIP | AF_MAX3 | AF_IMM | AF_ONES)
-  STA_ATTN_CASE(AF_SKIP | AF_MAX3 | AF_IMM | AF_ONES | AF_EMU)
-  STA_ATTN_CASE(AF_SKIP | AF_MAX3 | AF_IMM | AF_EMU)
+  STA_ATTN_CASE(AF_SKIP | AF_IMM)
+  STA_ATTN_CASE(AF_SKIP | AF_ONES)
+  STA_ATTN_CASE(AF_SKIP | AF_IMM | AF_ONES)
+  STA_ATTN_CASE(AF_SKIP | AF_IMM | AF_ONES | AF_EMU)
+  STA_ATTN_CASE(AF_SKIP | AF_IMM | AF_ONES | AF_2PASS)
+  STA_ATTN_CASE(AF_SKIP | AF_IMM | AF_2PASS)
+  STA_ATTN_CASE(AF_SKIP | AF_IMM | AF_ONES | AF_EMU | AF_2PASS)
 #undef STA_ATTN_CASE
   set_last_error("launch_attention: no kernel instance for this STA_ATTN_FEAT value");
   return 2;

@@ -74,6 +74,11 @@ int launch_pointmap_consumers(const float* pts3d, const float* conf, int V, int 
                               float* depth_out, float* conf_mean_out, void* scratch, cudaStream_t stream);
 int launch_depth_scale(const float* Di, const float* Dj, const float* ci, const float* cj, long long n, float* out2,
                        void* scratch, cudaStream_t stream);
+// pose_graph.cu: one Sim(3) pose-graph LM step (pose_graph.py:70-154, slam.py:108-140)
+size_t pose_graph_scratch_bytes(int num_nodes, int num_edges, int num_opt);
+int launch_pose_graph_lm_step(const float* nodes, int num_nodes, const long long* edges, const float* meas, const float* weights,
+                              int num_edges, const long long* opt_idx, int num_opt, double damping, double dmin, double dmax,
+                              float* nodes_out, double* info_out, void* scratch, cudaStream_t stream);
 int launch_im2col_3x3_s2(const bf16* in, bf16* out, int nimg, int H, int W, int C, cudaStream_t stream);
 int launch_copy_f32(const float* in, float* out, long long n, cudaStream_t stream);
 

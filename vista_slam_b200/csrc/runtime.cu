@@ -1692,6 +1692,20 @@ int sta_depth_scale(const float* Di, const float* Dj, const float* ci, const flo
 }
 
 // ---------------------------------------------------------------------------
+// Sim(3) pose-graph LM step (pose_graph.cu)
+// ---------------------------------------------------------------------------
+size_t sta_pose_graph_scratch_bytes(int num_nodes, int num_edges, int num_opt) {
+  return pose_graph_scratch_bytes(num_nodes, num_edges, num_opt);
+}
+int sta_pose_graph_lm_step(const float* nodes, int num_nodes, const int64_t* edges, const float* meas, const float* weights,
+                           int num_edges, const int64_t* opt_idx, int num_opt, double damping, double dmin, double dmax,
+                           float* nodes_out, double* info_out, void* scratch, void* stream) {
+  return launch_pose_graph_lm_step(nodes, num_nodes, reinterpret_cast<const long long*>(edges), meas, weights, num_edges,
+                                   reinterpret_cast<const long long*>(opt_idx), num_opt, damping, dmin, dmax, nodes_out,
+                                   info_out, scratch, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------
 // image preprocessing (preprocess.cu)
 // ---------------------------------------------------------------------------
 int sta_preprocess_shape(int H, int W, int res_w, int res_h, int w_edge, int h_edge, int* out_hw) {
