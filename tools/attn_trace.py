@@ -1,5 +1,9 @@
 """clock64 trace of one CTA of the attention kernel (run under gpurun): STA_ATTN_TRACE hands the kernel a device buffer.
     STA_ATTN_FEAT=15 python tools/attn_trace.py [n] [heads]
+
+The stamps exist only in the experimental builds of csrc/attention.cu (git history of round 2: the feature-template
+versions); the production kernel carries no trace code.  The traces that drove the round-2 decisions are kept in
+profiles/r02_attn_trace_*.log.
 """
 import os, sys, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
@@ -17,6 +21,8 @@ for _ in range(3):
     check(L.sta_op_attention(ptr(qkv), 3 * C, 0, ptr(qkv), 3 * C, C, ptr(qkv), 3 * C, 2 * C, ptr(out), C, batch, heads, n, n, 0, 0.125, 0, cur_stream()))
 torch.cuda.synchronize()
 b = buf.cpu().tolist()
+if not any(x > 0 for x in b):
+    sys.exit("this build of libsta_b200.so has no attention trace stamps (see the docstring)")
 t0 = min(x for x in b if x > 0)
 f = lambda e: [x - t0 if x > 0 else None for x in e]
 print("feat", os.environ.get("STA_ATTN_FEAT"), "n", n, "heads", heads)

@@ -3,6 +3,7 @@ per keyframe ONE _encode_image (B=1) and, per edge to an earlier keyframe, _deco
 2 x head_pts + estimate_intrinsic_from_pts3d -- first exactly as OnlineSLAM.regress_two_views (slam.py:153-189) issues
 them through the reference-shaped module methods, then through the batched keyframe step."""
 import argparse
+import json
 import os
 import sys
 import time
@@ -79,6 +80,30 @@ def main():
     ts = sorted(t_step[skip + 1:])
     print("batched keyframe step %dx%d: median %.3f ms/keyframe, p90 %.3f (encode + %d edges in one decode batch, %d samples)" %
           (H, W, med(ts), 1e3 * ts[int(0.9 * (len(ts) - 1))], a.edges, len(ts)), flush=True)
+
+    # ---- gated keyframe step: the reference's early-out (slam.py:169-170) kept, one host sync per keyframe ----
+    kg = KeyframeFrontend(m)
+    t_gate, kept = [], 0
+    # random-init confidences sit near 0.5: a threshold there exercises both outcomes
+    thres = 0.5
+    for i, im in enumerate(imgs):
+        sync(); t0 = time.perf_counter()
+        idx = kg.add_view(im, shape)
+        js = list(range(max(0, i - a.edges), i))
+        if js:
+            out = kg.regress_views_gated(idx, js, thres)
+            kept += sum(o[2] is not None for o in out)
+        sync(); t_gate.append(time.perf_counter() - t0)
+    tg = sorted(t_gate[skip + 1:])
+    print("gated keyframe step %dx%d: median %.3f ms/keyframe (%d of %d edges kept at thres %.2f)" %
+          (H, W, med(tg), kept, sum(min(a.edges, i) for i in range(len(imgs))), thres), flush=True)
+    print(json.dumps({"metric": "slam_keyframe_step_ms", "unit": "ms/keyframe (median)", "size": "%dx%d" % (W, H),
+                      "edges_per_keyframe": a.edges, "keyframes": a.keyframes,
+                      "workload": "cfg-3/4 stand-in: synthetic keyframe stream replaying the call sequence of slam.py:142-189,244-279 "
+                                  "(no dataset / pypose / DBoW3 in the container), random-init weights",
+                      "reference_shaped_calls_ms": enc_ms + a.edges * edge_ms, "encode_ms": enc_ms, "edge_ms": edge_ms,
+                      "batched_step_ms": med(ts), "batched_step_p90_ms": 1e3 * ts[int(0.9 * (len(ts) - 1))],
+                      "gated_step_ms": med(tg)}), flush=True)
 
 
 if __name__ == "__main__":

@@ -31,8 +31,6 @@
 
 #include <stdlib.h>
 
-#include <type_traits>
-
 namespace sta {
 
 namespace {
@@ -40,7 +38,7 @@ namespace {
 constexpr int ATT_THREADS = 384;  // warpgroup 0: TMA / MMA / 2 idle warps; warpgroups 1, 2: softmax groups A, B
 constexpr int KV_STAGES = 3;
 constexpr uint32_t TILE_BYTES = 128 * 64 * 2;  // 16 KB: [128 rows][64 bf16]
-// Q [group][2 buffers] | K x3 | V x3 | P [group] (two 64-key sub-tiles each) | ones [16][64] | barriers
+// Q [group][2 buffers] | K x3 | V x3 | P [group] (two 64-key sub-tiles each) | barriers
 constexpr uint32_t ATT_OFF_K = 4 * TILE_BYTES;
 constexpr uint32_t ATT_OFF_V = ATT_OFF_K + KV_STAGES * TILE_BYTES;
 constexpr uint32_t ATT_OFF_P = ATT_OFF_V + KV_STAGES * TILE_BYTES;
@@ -49,24 +47,13 @@ constexpr uint32_t ONES_BYTES = 16 * 128;
 constexpr uint32_t ATT_OFF_BAR = ATT_OFF_ONES + ONES_BYTES;
 constexpr uint32_t ATT_SMEM = ATT_OFF_BAR + 256;
 static_assert(ATT_SMEM <= 227 * 1024, "attention shared memory");
+// Feature bits (template parameter; STA_ATTN_FEAT selects an instance for A/B timing, tools/attn_ab.py):
+//   AF_SKIP  warps whose 32 query rows are all >= nq (ragged last query tile / dead second tile: the decoder's 769 rows are
+//            6 x 128 + 1) only keep the barrier protocol going -- no TMEM traffic, no math;
+//   AF_ONES  row sum l from the tensor core: one extra N = 16 MMA per key step multiplies P by a tile of ones, so l
+//            accumulates in TMEM next to O (and is the sum of exactly the bf16 P values that multiply V).
+enum AttnFeat : int { AF_SKIP = 1, AF_ONES = 8 };
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-constexpr float kScaleLog2Hd64 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e) for head_dim 64
-
-// Feature bits of the softmax warpgroups (template parameter; STA_ATTN_FEAT selects an instance for A/B timing)
-enum AttnFeat : int {
-  AF_SKIP = 1,   // warps whose 32 query rows are all >= nq only keep the barrier protocol going (no TMEM loads, no math):
-                 // the decoder's 769 = 6 x 128 + 1 rows then cost 6.25 instead of 8 tiles of softmax work
-  AF_MAX3 = 2,   // (unused: the compiler already fuses the fmaxf chains into 3-input FMNMX3)
-  AF_IMM = 4,    // scale * log2(e) as an immediate operand of the FFMA (only when scale == 0.125)
-  AF_ONES = 8,   // row sum l from the tensor core: one extra N = 16 MMA per key step multiplies P by a tile of ones, so
-                 // l accumulates in TMEM next to O (and is the sum of exactly the bf16 P values that multiply V)
-  AF_EMU = 16,   // 2 of every 8 exponentials on the FMA pipe (ex2_fma) instead of the 16-lane/clk MUFU
-  AF_2PASS = 64, // the score row is read from TMEM twice, 32 columns at a time (pass 1: row maximum, pass 2: exponentials),
-                 // instead of being held in 128 registers: ptxas allocates for the launch-bound cap (168 registers, it does
-                 // not widen for setmaxnreg.inc), so the one-pass exp2 loop is register-starved; the two-pass loops are
-                 // software-pipelined (TMEM load of chunk c+1 under the math of chunk c).  S is released together with P
-                 // (no s_free barrier): the MMA thread issues P_t V and then S_t(n+1) back to back.
-};
 
 struct AttnParams {
   int nq, nk, batch, heads, qpairs, kv_batch_shift;
@@ -76,7 +63,6 @@ struct AttnParams {
   float scale_log2;
   __nv_bfloat16* out;
   long long ldo;
-  long long* dbg;  // optional clock64 trace (env STA_ATTN_TRACE = device address), else null
 };
 
 template <int FEAT>
@@ -89,7 +75,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint8_t* sK = smem + ATT_OFF_K;
   uint8_t* sV = smem + ATT_OFF_V;
   uint8_t* sP = smem + ATT_OFF_P;  // group t at sP + t * 2 * TILE_BYTES
-  uint8_t* sOnes = smem + ATT_OFF_ONES;
+  [[maybe_unused]] uint8_t* sOnes = smem + ATT_OFF_ONES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_OFF_BAR);
   uint64_t* q_full = bars + 0;    // [2 groups][2 buffers]
   uint64_t* q_empty = bars + 4;   // [2][2]
@@ -142,9 +128,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) l_A [384,400) l_B [400,416)
+  // columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) l_A [384,400) l_B [400,416) (AF_ONES)
   pdl_wait();
   pdl_launch_dependents();
+
 
   auto decode = [&](int w, int& q0, int& head, int& b, int& kvb) {
     const int qp = w % p.qpairs;
@@ -157,7 +144,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int my_items = (p.nitems > static_cast<int>(blockIdx.x))
                            ? (p.nitems - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
                            : 0;
-  const bool trace_cta = p.dbg != nullptr && blockIdx.x == 0;
 
   // register re-distribution: the softmax threads keep a whole 128-score row in registers
   if (warp < 4) {
@@ -194,11 +180,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_s16 = make_idesc_bf16(128, 16, 0, 0);  // narrow tail tile (<= 16 valid keys); row-sum MMA
+      constexpr uint32_t idesc_s16 = make_idesc_bf16(128, 16, 0, 0);  // narrow tail tile (<= 16 valid keys)
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);    // B (= V) is MN-major
       const bool narrow_tail = (p.nk - (T - 1) * 128) <= 16;
       const int total = my_items * T;  // key-tile steps of this CTA; step n = it * T + j
-      const uint64_t ones_desc = make_smem_desc_sw128(smem_u32(sOnes));
       // state of the NEXT S to issue (same for both groups; advanced after group B)
       int s_it = 0, s_j = 0, s_st = 0;
       uint32_t s_ph = 0;
@@ -228,53 +213,33 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       int v_st = 0, j = 0;
       uint32_t v_ph = 0;
       for (int n = 0; n < total; ++n) {
-        const bool trc = trace_cta && n < 32;
-        // S_t(n+1) as soon as group t holds S_t(n) in registers (2PASS: issued right after P_t(n) V instead, see below)
-        if (!(FEAT & AF_2PASS) && n + 1 < total) {
+        // S_t(n+1) as soon as group t holds S_t(n) in registers
+        if (n + 1 < total) {
           for (int t = 0; t < 2; ++t) {
-            if (trc) p.dbg[16 * n + 4 * t + 0] = clock64();
             mbar_wait(&s_free[t], n & 1);
-            if (trc) p.dbg[16 * n + 4 * t + 1] = clock64();
             issue_s(t);
-            if (trc) p.dbg[16 * n + 4 * t + 2] = clock64();
           }
         }
         // O_t (+)= P_t(n) V(n) as soon as group t has written P_t(n)
         for (int t = 0; t < 2; ++t) {
-          if (trc) p.dbg[16 * n + 8 + 4 * t + 0] = clock64();
           mbar_wait(&p_full[t], n & 1);
           if (t == 0) mbar_wait(&v_full[v_st], v_ph);
-          if (trc) p.dbg[16 * n + 8 + 4 * t + 1] = clock64();
           tc_fence_after();
           const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + v_st * TILE_BYTES));
           const uint64_t pdesc0 = make_smem_desc_sw128(smem_u32(sP + t * 2 * TILE_BYTES));
           const uint64_t pdesc1 = make_smem_desc_sw128(smem_u32(sP + t * 2 * TILE_BYTES + TILE_BYTES));
           const uint32_t d = tmem_base + 256 + t * 64;
-          const uint32_t dl = tmem_base + 384 + t * 16;
-          // V advances 16 keys = 16 rows x 128 B = 2048 B per step; the first key tile of an item overwrites O.
-          // Row sums (AF_ONES): l_t (+)= P_t(n) 1 -- all 16 columns equal; the ones tile is the same for every key step.
-          const uint32_t acc0 = j > 0 ? 1u : 0u;
-          if (narrow_tail && j == T - 1) {  // a narrow tail tile holds <= 16 keys: one step
-            umma_bf16(d, pdesc0, vdesc, idesc_o, acc0);
-            if constexpr (FEAT & AF_ONES) umma_bf16(dl, pdesc0, ones_desc, idesc_s16, acc0);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
-              umma_bf16(d, pd, vdesc + (2048 >> 4) * k, idesc_o, k > 0 ? 1u : acc0);
-            }
-            if constexpr (FEAT & AF_ONES) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                umma_bf16(dl, (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3), ones_desc, idesc_s16, k > 0 ? 1u : acc0);
-            }
+          const int ksteps = (narrow_tail && j == T - 1) ? 1 : 8;  // a narrow tail tile holds <= 16 keys
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
+            // V advances 16 keys = 16 rows x 128 B = 2048 B per step; first key tile of an item overwrites O
+            umma_bf16(d, pd, vdesc + (2048 >> 4) * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+            // row sums: l_t (+)= P_t(n) 1 (all 16 columns equal; the ones tile is the same for every key step)
+            if constexpr (FEAT & AF_ONES)
+              umma_bf16(tmem_base + 384 + t * 16, pd, make_smem_desc_sw128(smem_u32(sOnes)), idesc_s16, (j > 0 || k > 0) ? 1u : 0u);
           }
           if (t == 1) umma_commit(&v_empty[v_st]);
           umma_commit(&o_full[t]);
-          if constexpr (FEAT & AF_2PASS) {
-            if (n + 1 < total) issue_s(t);  // group t finished reading S_t(n) before it signalled p_full
-          }
-          if (trc) p.dbg[16 * n + 8 + 4 * t + 2] = clock64();
         }
         if (++v_st == KV_STAGES) { v_st = 0; v_ph ^= 1; }
         if (++j == T) j = 0;
@@ -291,9 +256,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int rx = r & 7;
     const uint32_t tS = tmem_base + lane_addr + grp * 128;       // this group's S buffer
     const uint32_t tO = tmem_base + lane_addr + 256 + grp * 64;  // this group's O accumulator
-    const uint32_t tL = tmem_base + lane_addr + 384 + grp * 16;  // this group's row sums (AF_ONES)
+    [[maybe_unused]] const uint32_t tL = tmem_base + lane_addr + 384 + grp * 16;  // this group's row sums (AF_ONES)
     uint8_t* prow = sP + grp * 2 * TILE_BYTES + r * 128;         // this group's P buffer, row r
-    const float scale_log2 = (FEAT & AF_IMM) ? kScaleLog2Hd64 : p.scale_log2;
     int n = 0;  // key-tile step counter (barrier parities)
     // Enforced ping-pong of the MUFU-bound phase (STA_ATTN_PINGPONG, default on): the two groups take turns with the
     // exponentials -- group t waits on named barrier 3 + t before its exp2 loop and hands the turn to the other
@@ -304,69 +268,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     auto turn_wait = [&]() { if (pingpong) named_bar_sync(3 + grp, 256); };
     auto turn_pass = [&]() { if (pingpong) named_bar_arrive(3 + (grp ^ 1), 256); };
     if (pingpong && grp == 1) named_bar_arrive(3, 256);  // group A goes first
-    const bool trace_thr = trace_cta && quarter == 0 && lane == 0;
-    // rescale O (and l) in place by `factor` (1 for the rows whose reference maximum did not move)
-    auto rescale_acc = [&](float factor) {
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t o[32];
-        tmem_ld32(tO + c, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-        tmem_st32(tO + c, o);
-      }
-      if constexpr (FEAT & AF_ONES) {
-        const uint32_t lv = tmem_ld1(tL);
-        tmem_ld_wait();
-        tmem_st1(tL, __float_as_uint(__uint_as_float(lv) * factor));
-      }
-      tmem_st_wait();
-    };
-
-    // P = exp2(S*c - m) for NCH 16-byte chunks of 8 keys -> bf16, 128B-swizzled K-major tile; returns the row sum
-    auto exp_store = [&](const uint32_t* s, float m_used, auto nch_tag, int chunk0 = 0) -> float {
-      constexpr int NCH = decltype(nch_tag)::value;
-      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float x = fmaf(__uint_as_float(s[8 * c + i]), scale_log2, -m_used);
-          if ((FEAT & AF_EMU) && (i == 3 || i == 7)) e[i] = ex2_fma(x);
-          else e[i] = ex2_approx(x);
-        }
-        if constexpr (!(FEAT & AF_ONES)) {
-          rs0 += e[0] + e[4];
-          rs1 += e[1] + e[5];
-          rs2 += e[2] + e[6];
-          rs3 += e[3] + e[7];
-        }
-        uint4 q;
-        q.x = pack_bf16x2(e[0], e[1]);
-        q.y = pack_bf16x2(e[2], e[3]);
-        q.z = pack_bf16x2(e[4], e[5]);
-        q.w = pack_bf16x2(e[6], e[7]);
-        const int cc = chunk0 + c;
-        *reinterpret_cast<uint4*>(prow + (cc >> 3) * TILE_BYTES + (((cc & 7) ^ rx) << 4)) = q;
-      }
-      return (rs0 + rs1) + (rs2 + rs3);
-    };
 
     for (int it = 0; it < my_items; ++it) {
       int q0, head, b, kvb;
       decode(static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x), q0, head, b, kvb);
-      // AF_SKIP: all 32 rows of this warp lie beyond nq (ragged last query tile, or a dead second tile): the warp only
-      // keeps the barrier protocol in step -- the same waits and arrivals as a live warp, in the same order, but no TMEM
-      // traffic and no math.  Its P rows keep stale values: rows of O are independent and rows >= nq are never stored.
+      // AF_SKIP: all 32 rows of this warp lie beyond nq: keep the barrier protocol in step (the same waits and arrivals as a
+      // live warp, in the same order) but do no TMEM traffic and no math.  The warp's P rows keep stale values: rows of O
+      // are independent and rows >= nq are never stored.
       if ((FEAT & AF_SKIP) && (q0 + grp * 128 + quarter * 32 >= p.nq)) {
         for (int j = 0; j < T; ++j, ++n) {
           mbar_wait(&s_full[grp], n & 1);
           tc_fence_before();
           __syncwarp();
-          if (!(FEAT & AF_2PASS) && lane == 0) mbar_arrive(&s_free[grp]);
+          if (lane == 0) mbar_arrive(&s_free[grp]);
           if (j > 0) mbar_wait(&o_full[grp], (n - 1) & 1);
           if (j == 0 && it > 0) named_bar_sync(1 + grp, 128);
           turn_wait();
@@ -382,12 +296,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       float l = 0.f;
 
       for (int j = 0; j < T; ++j, ++n) {
-        const bool trc = trace_thr && n < 30;
         const int nvalid = p.nk - j * 128;  // >= 1
-        if (trc) p.dbg[512 + grp * 256 + 8 * n + 0] = clock64();
         mbar_wait(&s_full[grp], n & 1);
         tc_fence_after();
-        if (trc) p.dbg[512 + grp * 256 + 8 * n + 1] = clock64();
         if (nvalid <= 16 && j == T - 1) {
           // ---- narrow tail tile: S is 128 x 16, P V uses a single 16-key step ----
           uint32_t s16[16];
@@ -395,14 +306,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (!(FEAT & AF_2PASS) && lane == 0) mbar_arrive(&s_free[grp]);
+          if (lane == 0) mbar_arrive(&s_free[grp]);
           float mxn = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             if (i >= nvalid) s16[i] = 0xff800000u;
             mxn = fmaxf(mxn, __uint_as_float(s16[i]));
           }
-          const float m_true = mxn * scale_log2;
+          const float m_true = mxn * p.scale_log2;
           const bool raise = m_true > m_used + kRescaleThreshold;
           const float m_new = raise ? m_true : m_used;
           const float factor = raise ? ex2_approx(m_used - m_new) : 1.0f;
@@ -410,83 +321,52 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           m_used = m_new;
           if (j > 0) {
             mbar_wait(&o_full[grp], (n - 1) & 1);
-            if (__any_sync(0xffffffffu, raise)) rescale_acc(factor);
+            if (__any_sync(0xffffffffu, raise)) {
+              tc_fence_after();
+#pragma unroll
+              for (int c = 0; c < 64; c += 32) {
+                uint32_t o[32];
+                tmem_ld32(tO + c, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                tmem_st32(tO + c, o);
+              }
+              if constexpr (FEAT & AF_ONES) {
+                const uint32_t lv = tmem_ld1(tL);
+                tmem_ld_wait();
+                tmem_st1(tL, __float_as_uint(__uint_as_float(lv) * factor));
+              }
+              tmem_st_wait();
+            }
           }
           if (j == 0 && it > 0) {
             if (warp == 4 + 4 * grp && lane == 0) tma_store_wait_read();
             named_bar_sync(1 + grp, 128);
           }
+          float rs = 0.f;
           turn_wait();
-          l += exp_store(s16, m_used, std::integral_constant<int, 2>{});
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              e[i] = ex2_approx(fmaf(__uint_as_float(s16[8 * c + i]), p.scale_log2, -m_used));
+              if constexpr (!(FEAT & AF_ONES)) rs += e[i];
+            }
+            uint4 q;
+            q.x = pack_bf16x2(e[0], e[1]);
+            q.y = pack_bf16x2(e[2], e[3]);
+            q.z = pack_bf16x2(e[4], e[5]);
+            q.w = pack_bf16x2(e[6], e[7]);
+            *reinterpret_cast<uint4*>(prow + ((c ^ rx) << 4)) = q;
+          }
           turn_pass();
+          l += rs;
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_full[grp]);
-          continue;
-        }
-        if constexpr (FEAT & AF_2PASS) {
-          // ---- pass 1: row maximum, 32 columns at a time; the load of chunk c+1 is in flight under the maxima of chunk c ----
-          uint32_t buf[2][32];
-          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-          tmem_ld32(tS, buf[0]);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            tmem_ld_wait();
-            if (c < 3) tmem_ld32(tS + 32 * (c + 1), buf[(c + 1) & 1]);
-            uint32_t* v = buf[c & 1];
-            if (nvalid < 128) {  // ragged last key tile
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (32 * c + i >= nvalid) v[i] = 0xff800000u;
-            }
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              mx0 = fmaxf(mx0, __uint_as_float(v[i]));
-              mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
-              mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
-              mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
-            }
-          }
-          if (trc) p.dbg[512 + grp * 256 + 8 * n + 2] = clock64();
-          const float m_true = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
-          const bool raise = m_true > m_used + kRescaleThreshold;  // always true on the first tile (m_used = -inf)
-          const float m_new = raise ? m_true : m_used;
-          const float factor = raise ? ex2_approx(m_used - m_new) : 1.0f;
-          l *= factor;
-          m_used = m_new;
-          if (trc) p.dbg[512 + grp * 256 + 8 * n + 3] = clock64();
-          if (j > 0) {
-            mbar_wait(&o_full[grp], (n - 1) & 1);
-            if (__any_sync(0xffffffffu, raise)) rescale_acc(factor);
-          }
-          if (j == 0 && it > 0) {
-            if (warp == 4 + 4 * grp && lane == 0) tma_store_wait_read();
-            named_bar_sync(1 + grp, 128);
-          }
-          if (trc) p.dbg[512 + grp * 256 + 8 * n + 4] = clock64();
-          turn_wait();
-          // ---- pass 2: exponentials, again 32 columns at a time with the next chunk's load in flight ----
-          tc_fence_after();
-          tmem_ld32(tS, buf[0]);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            tmem_ld_wait();
-            if (c < 3) tmem_ld32(tS + 32 * (c + 1), buf[(c + 1) & 1]);
-            uint32_t* v = buf[c & 1];
-            if (nvalid < 128) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (32 * c + i >= nvalid) v[i] = 0xff800000u;
-            }
-            l += exp_store(v, m_used, std::integral_constant<int, 4>{}, 4 * c);
-          }
-          turn_pass();
-          fence_proxy_async_smem();
-          tc_fence_before();  // orders this thread's TMEM loads of S (and the O rescale) before the MMAs that follow p_full
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[grp]);
-          if (trc) p.dbg[512 + grp * 256 + 8 * n + 5] = clock64();
           continue;
         }
         // ---- the whole score row into registers; release the S buffer for the next Q K^T ----
@@ -505,13 +385,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[grp]);
-        if (trc) p.dbg[512 + grp * 256 + 8 * n + 2] = clock64();
         if (nvalid < 128) {  // ragged last key tile: masked scores contribute exp2(-inf) = 0
 #pragma unroll
           for (int i = 0; i < 128; ++i)
             if (i >= nvalid) s[i] = 0xff800000u;
         }
-        // ---- row maximum (4 independent chains; the compiler fuses pairs into FMNMX3) ----
+        // ---- row maximum (4 independent chains) ----
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 128; i += 4) {
@@ -520,40 +399,71 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
           mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
         }
-        const float m_true = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+        const float m_true = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
         // lazy rescaling: keep the old reference maximum unless the row maximum grew by more than 2^8
         const bool raise = m_true > m_used + kRescaleThreshold;  // always true on the first tile (m_used = -inf)
         const float m_new = raise ? m_true : m_used;
         const float factor = raise ? ex2_approx(m_used - m_new) : 1.0f;  // first tile: exp2(-inf) = 0
         l *= factor;
         m_used = m_new;
-        if (trc) p.dbg[512 + grp * 256 + 8 * n + 3] = clock64();
         // the previous P V of this group must be complete before P is overwritten (and before O is rescaled)
         if (j > 0) {
           mbar_wait(&o_full[grp], (n - 1) & 1);
-          if (__any_sync(0xffffffffu, raise)) rescale_acc(factor);
+          if (__any_sync(0xffffffffu, raise)) {
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+              uint32_t o[32];
+              tmem_ld32(tO + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+              tmem_st32(tO + c, o);
+            }
+            if constexpr (FEAT & AF_ONES) {
+              const uint32_t lv = tmem_ld1(tL);
+              tmem_ld_wait();
+              tmem_st1(tL, __float_as_uint(__uint_as_float(lv) * factor));
+            }
+            tmem_st_wait();
+          }
         }
         if (j == 0 && it > 0) {
           // the previous item's output tile was staged in this P buffer: its TMA store must have read it
           if (warp == 4 + 4 * grp && lane == 0) tma_store_wait_read();
           named_bar_sync(1 + grp, 128);
         }
-        if (trc) p.dbg[512 + grp * 256 + 8 * n + 4] = clock64();
+        // ---- P = exp2(S*c - m_used) -> bf16, 128B-swizzled K-major tile in this group's P buffer ----
+        float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
         turn_wait();
-        l += exp_store(s, m_used, std::integral_constant<int, 16>{});
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {  // 16-byte chunks of 8 keys
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(s[8 * c + i]), p.scale_log2, -m_used));
+          if constexpr (!(FEAT & AF_ONES)) {
+            rs0 += e[0] + e[4];
+            rs1 += e[1] + e[5];
+            rs2 += e[2] + e[6];
+            rs3 += e[3] + e[7];
+          }
+          uint4 q;
+          q.x = pack_bf16x2(e[0], e[1]);
+          q.y = pack_bf16x2(e[2], e[3]);
+          q.z = pack_bf16x2(e[4], e[5]);
+          q.w = pack_bf16x2(e[6], e[7]);
+          *reinterpret_cast<uint4*>(prow + (c >> 3) * TILE_BYTES + (((c & 7) ^ rx) << 4)) = q;
+        }
         turn_pass();
+        l += (rs0 + rs1) + (rs2 + rs3);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[grp]);
-        if (trc) p.dbg[512 + grp * 256 + 8 * n + 5] = clock64();
       }
       // ---- item epilogue: O / l -> bf16 -> 128B-swizzled smem tile (the idle P buffer) -> one TMA store ----
-      const bool trce = trace_thr && it < 6;
-      if (trce) p.dbg[1100 + grp * 32 + it * 4 + 0] = clock64();
       mbar_wait(&o_full[grp], (n - 1) & 1);
       tc_fence_after();
-      if (trce) p.dbg[1100 + grp * 32 + it * 4 + 1] = clock64();
       if constexpr (FEAT & AF_ONES) {
         l = __uint_as_float(tmem_ld1(tL));
         tmem_ld_wait();
@@ -582,7 +492,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tma_store_3d(&tmO, sP + grp * 2 * TILE_BYTES, head * 64, q0 + grp * 128, b);
         tma_store_commit();
       }
-      if (trce) p.dbg[1100 + grp * 32 + it * 4 + 2] = clock64();
     }
     if (pingpong && grp == 0) named_bar_sync(3, 256);  // consume group B's last hand-over
     if (warp == 4 + 4 * grp && lane == 0) tma_store_wait_all();
@@ -828,8 +737,8 @@ int make_qkv_map(CUtensorMap* m, const bf16* base, long long ld, int ntok, int b
 
 }  // namespace
 
-// default feature set (updated from the A/B measurements in profiles/)
-constexpr int kDefaultFeat = AF_SKIP | AF_IMM | AF_ONES;
+// default feature set (from the same-box A/B measurements in profiles/r02_attn_ab_*.log)
+constexpr int kDefaultFeat = AF_SKIP;
 
 int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   STA_REQUIRE(a.batch > 0 && a.heads > 0 && a.nq > 0 && a.nk > 0, "empty attention problem");
@@ -860,10 +769,12 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   p.ldo = a.ldo;
   p.heads = a.heads;
   const size_t row0_smem = (((a.nk + 3) & ~3) + 16 + 32 * 64) * sizeof(float);
-  static int pingpong_env = -1;
+  static int pingpong_env = -1, feat_env = -2;
   if (pingpong_env < 0) {
     const char* e = getenv("STA_ATTN_PINGPONG");  // 0 disables (A/B timing)
     pingpong_env = (e && e[0] == '0') ? 0 : 1;
+    e = getenv("STA_ATTN_FEAT");  // feature set of the softmax warpgroups (A/B timing; see AttnFeat)
+    feat_env = e ? atoi(e) : -1;
   }
   p.pingpong = pingpong_env;
   const int split = (a.split_first_row && a.nq > 1 && row0_smem <= 48 * 1024) ? 1 : 0;
@@ -876,39 +787,31 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
                               a.ldk, a.k_col0, a.v, a.ldv, a.v_col0, a.out, a.ldo, a.nq, a.nk, a.batch, a.kv_batch_shift,
                               p.scale_log2));
   }
-  const int grid = p.nitems < num_sms() ? p.nitems : num_sms();
-  {
-    const char* e = getenv("STA_ATTN_TRACE");
-    p.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+  const int feat = feat_env >= 0 ? feat_env : kDefaultFeat;
+  // Work items w = (query-tile pair fastest, head, sample) are dealt round-robin to the CTAs (w = blockIdx + it * grid), so
+  // that neighbouring CTAs work on the pairs of ONE (sample, head) at the same time and share its K / V tiles in L2.  The
+  // last pair of a 128k+1-row problem (the decoder's 769 rows) is much cheaper than the others (AF_SKIP): the grid is made
+  // coprime with the pair count, otherwise a CTA would only ever see one kind of item (148 = 4 x 37) and the cheap ones
+  // would not shorten the kernel at all.
+  int grid = p.nitems < num_sms() ? p.nitems : num_sms();
+  if ((feat & AF_SKIP) && (p.nq - p.q_row0) % 256 != 0 && p.nitems > grid) {
+    auto gcd = [](int x, int y) { while (y) { const int t = x % y; x = y; y = t; } return x; };
+    while (grid > 1 && gcd(grid, p.qpairs) != 1) --grid;
   }
-  // feature set of the softmax warpgroups (STA_ATTN_FEAT overrides for A/B timing; see AttnFeat)
-  static int feat_env = -2;
-  if (feat_env == -2) {
-    const char* e = getenv("STA_ATTN_FEAT");
-    feat_env = e ? atoi(e) : -1;
-  }
-  int feat = feat_env >= 0 ? feat_env : kDefaultFeat;
-  if (a.scale != 0.125f) feat &= ~AF_IMM;
-#define STA_ATTN_CASE(F)                                                                                          \
-  if (feat == (F)) {                                                                                              \
-    static PerDeviceOnce once;                                                                                    \
-    STA_CHECK_CUDA(once.run([&] {                                                                                 \
-      return cudaFuncSetAttribute(attention_fwd_kernel<(F)>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                  (int)ATT_SMEM);                                                                 \
-    }));                                                                                                          \
-    STA_CHECK_CUDA(launch_pdl(attention_fwd_kernel<(F)>, dim3(grid), dim3(ATT_THREADS), ATT_SMEM, stream, 1, tmQ, \
-                              tmK, tmV, tmO, p, a.q_col0, a.k_col0, a.v_col0));                                   \
-    return 0;                                                                                                     \
+#define STA_ATTN_CASE(F)                                                                                                    \
+  if (feat == (F)) {                                                                                                        \
+    static PerDeviceOnce once; /* the opt-in is per device, not per process */                                              \
+    STA_CHECK_CUDA(once.run([&] {                                                                                           \
+      return cudaFuncSetAttribute(attention_fwd_kernel<(F)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);   \
+    }));                                                                                                                    \
+    STA_CHECK_CUDA(launch_pdl(attention_fwd_kernel<(F)>, dim3(grid), dim3(ATT_THREADS), ATT_SMEM, stream, 1, tmQ, tmK, tmV, \
+                              tmO, p, a.q_col0, a.k_col0, a.v_col0));                                                       \
+    return 0;                                                                                                               \
   }
   STA_ATTN_CASE(0)
   STA_ATTN_CASE(AF_SKIP)
-  STA_ATTN_CASE(AF_SKIP | AF_IMM)
+  STA_ATTN_CASE(AF_ONES)
   STA_ATTN_CASE(AF_SKIP | AF_ONES)
-  STA_ATTN_CASE(AF_SKIP | AF_IMM | AF_ONES)
-  STA_ATTN_CASE(AF_SKIP | AF_IMM | AF_ONES | AF_EMU)
-  STA_ATTN_CASE(AF_SKIP | AF_IMM | AF_ONES | AF_2PASS)
-  STA_ATTN_CASE(AF_SKIP | AF_IMM | AF_2PASS)
-  STA_ATTN_CASE(AF_SKIP | AF_IMM | AF_ONES | AF_EMU | AF_2PASS)
 #undef STA_ATTN_CASE
   set_last_error("launch_attention: no kernel instance for this STA_ATTN_FEAT value");
   return 2;

@@ -202,7 +202,9 @@ struct StaModel {
   size_t io_bytes = 0;
   static constexpr int kMaxHostChunks = 32;
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the host entry point
-  cudaEvent_t ev_in[kMaxHostChunks] = {}, ev_done[kMaxHostChunks] = {}, ev_part[kMaxHostChunks][4] = {}, ev_start = nullptr;
+  static constexpr int kMaxParts = 4;  // DPT parts per view in the host entry point (D2H of a part overlaps the next part)
+  cudaEvent_t ev_in[kMaxHostChunks] = {}, ev_done[kMaxHostChunks] = {}, ev_part[kMaxHostChunks][2 * kMaxParts] = {},
+              ev_start = nullptr;
   int64_t launches = 0;
   int max_pairs_per_chunk = 16;
   int rp_K = 0, rp_H = 0, rp_W = 0;  // state between sta_regress_pairs_begin and _finish
@@ -910,6 +912,9 @@ int check_ready(StaModel* m) {
   return 0;
 }
 
+// DPT parts per view in the host entry point: the tile counts of the head convolutions stay >> 148 down to 4 images per part
+int host_dpt_parts(int B) { return B >= 8 ? StaModel::kMaxParts : (B >= 2 ? 2 : 1); }
+
 int forward_chunk(const Ctx& c, const void* img1, const void* img2, int img_is_bf16, int B, int H, int W,
                   float* pts3d, float* conf, float* pose, float* pose_conf, int B_total,
                   cudaEvent_t* ev_parts = nullptr) {
@@ -939,11 +944,11 @@ int forward_chunk(const Ctx& c, const void* img1, const void* img2, int img_is_b
     RUN(launch_pose_head(d.xd + static_cast<long long>(B) * M * kDecDim, static_cast<long long>(M) * kDecDim, B, 1,
                          kLnEps, m->pose, pose + static_cast<long long>(B_total) * 16, pose_conf + B_total, c.st));
   }
-  // DPT heads: view 1 images then view 2 images (outputs are [2][B_total] blocks).  The host entry point passes four
-  // events: each view is then processed in two halves and an event is recorded after every part, so that the D2H copy
-  // of one part runs under the head of the next and only the last quarter of the outputs is exposed.
+  // DPT heads: view 1 images then view 2 images (outputs are [2][B_total] blocks).  The host entry point passes events:
+  // each view is then processed in `halves` parts (host_dpt_parts) and an event is recorded after every part, so that the
+  // D2H copy of one part runs under the head of the next and only the last part of the outputs (1/8 at B >= 8) is exposed.
   const long long px = static_cast<long long>(H) * W;
-  const int halves = (ev_parts && B >= 2) ? 2 : 1;
+  const int halves = ev_parts ? host_dpt_parts(B) : 1;
   for (int v = 0; v < 2; ++v) {
     for (int hf = 0; hf < halves; ++hf) {
       const int i0 = hf * (B / halves), nb = (hf == halves - 1) ? B - i0 : B / halves;
@@ -953,7 +958,7 @@ int forward_chunk(const Ctx& c, const void* img1, const void* img2, int img_is_b
                   d.hook[2] + tok0 * 768 * bm, pts3d + (static_cast<long long>(v) * B_total + i0) * px * 3,
                   conf + (static_cast<long long>(v) * B_total + i0) * px));
       ws.off = save;
-      if (ev_parts) STA_CHECK_CUDA(cudaEventRecord(ev_parts[v * 2 + hf], c.st));
+      if (ev_parts) STA_CHECK_CUDA(cudaEventRecord(ev_parts[v * halves + hf], c.st));
     }
   }
   return 0;
@@ -1039,7 +1044,7 @@ void sta_destroy(StaModel* m) {
     for (int i = 0; i < StaModel::kMaxHostChunks; ++i) {
       cudaEventDestroy(m->ev_in[i]);
       cudaEventDestroy(m->ev_done[i]);
-      for (int k = 0; k < 4; ++k) cudaEventDestroy(m->ev_part[i][k]);
+      for (int k = 0; k < 2 * StaModel::kMaxParts; ++k) cudaEventDestroy(m->ev_part[i][k]);
     }
     cudaEventDestroy(m->ev_start);
   }
@@ -1516,7 +1521,8 @@ int sta_forward_pairs_host(StaModel* m, const void* img1_host, const void* img2_
     for (int i = 0; i < StaModel::kMaxHostChunks; ++i) {
       STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming));
       STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
-      for (int k = 0; k < 4; ++k) STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_part[i][k], cudaEventDisableTiming));
+      for (int k = 0; k < 2 * StaModel::kMaxParts; ++k)
+        STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_part[i][k], cudaEventDisableTiming));
     }
     STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
   }
@@ -1570,11 +1576,11 @@ int sta_forward_pairs_host(StaModel* m, const void* img1_host, const void* img2_
                       d_pts + static_cast<size_t>(b0) * px * 3, d_conf + static_cast<size_t>(b0) * px,
                       d_pose + static_cast<size_t>(b0) * 16, d_pconf + b0, B, m->ev_part[c]));
     STA_CHECK_CUDA(cudaEventRecord(m->ev_done[c], st));
-    const int halves = nb >= 2 ? 2 : 1;  // must mirror forward_chunk
+    const int halves = host_dpt_parts(nb);  // mirrors forward_chunk
     for (int v = 0; v < 2; ++v) {
       for (int hf = 0; hf < halves; ++hf) {
         const int i0 = hf * (nb / halves), ni = (hf == halves - 1) ? nb - i0 : nb / halves;
-        STA_CHECK_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_part[c][v * 2 + hf], 0));
+        STA_CHECK_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_part[c][v * halves + hf], 0));
         const size_t o = static_cast<size_t>(v) * B + b0 + i0;
         STA_CHECK_CUDA(cudaMemcpyAsync(pts3d_out_host + o * px * 3, d_pts + o * px * 3, ni * px * 3 * sizeof(float),
                                        cudaMemcpyDeviceToHost, m->s_out));
