@@ -52,7 +52,13 @@ static_assert(ATT_SMEM <= 227 * 1024, "attention shared memory");
 //            6 x 128 + 1) only keep the barrier protocol going -- no TMEM traffic, no math;
 //   AF_ONES  row sum l from the tensor core: one extra N = 16 MMA per key step multiplies P by a tile of ones, so l
 //            accumulates in TMEM next to O (and is the sum of exactly the bf16 P values that multiply V).
-enum AttnFeat : int { AF_SKIP = 1, AF_ONES = 8 };
+//   AF_PTMEM P stays in tensor memory: the softmax threads write the bf16 probabilities with tcgen05.st into 64 TMEM columns
+//            per query tile and the P V MMAs take their A operand from there (tcgen05.mma with a TMEM A operand), so an
+//            N = 64 MMA no longer has to stream a 4 KB slice of P out of shared memory (it is shared-memory-bandwidth
+//            bound otherwise: ~64 clk instead of 32), and the softmax needs no st.shared / fence.proxy.async.
+//            TMEM: S 2 x 128 | O 2 x 64 | P 2 x 64 = 512 columns (hence exclusive with AF_ONES).
+//   AF_EMU   2 of every 8 exponentials on the FMA pipe (ex2_fma, degree-3 polynomial) instead of the 16-lane/clk MUFU.
+enum AttnFeat : int { AF_SKIP = 1, AF_ONES = 8, AF_PTMEM = 16, AF_EMU = 32 };
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 struct AttnParams {
@@ -230,6 +236,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint64_t pdesc1 = make_smem_desc_sw128(smem_u32(sP + t * 2 * TILE_BYTES + TILE_BYTES));
           const uint32_t d = tmem_base + 256 + t * 64;
           const int ksteps = (narrow_tail && j == T - 1) ? 1 : 8;  // a narrow tail tile holds <= 16 keys
+          if constexpr (FEAT & AF_PTMEM) {
+            // A = P_t straight from tensor memory: 16 keys = 8 packed columns per step
+            const uint32_t tp = tmem_base + 384 + t * 64;
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16_ts(d, tp + 8 * k, vdesc + (2048 >> 4) * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          } else
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
             // V advances 16 keys = 16 rows x 128 B = 2048 B per step; first key tile of an item overwrites O
@@ -257,6 +269,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tS = tmem_base + lane_addr + grp * 128;       // this group's S buffer
     const uint32_t tO = tmem_base + lane_addr + 256 + grp * 64;  // this group's O accumulator
     [[maybe_unused]] const uint32_t tL = tmem_base + lane_addr + 384 + grp * 16;  // this group's row sums (AF_ONES)
+    [[maybe_unused]] const uint32_t tP = tmem_base + lane_addr + 384 + grp * 64;  // this group's P tile (AF_PTMEM)
     uint8_t* prow = sP + grp * 2 * TILE_BYTES + r * 128;         // this group's P buffer, row r
     int n = 0;  // key-tile step counter (barrier parities)
     // Enforced ping-pong of the MUFU-bound phase (STA_ATTN_PINGPONG, default on): the two groups take turns with the
@@ -281,14 +294,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_free[grp]);
+          __syncwarp();  // the named barriers below are warp-aligned: reconverge after the one-lane arrival
           if (j > 0) mbar_wait(&o_full[grp], (n - 1) & 1);
+          __syncwarp();
           if (j == 0 && it > 0) named_bar_sync(1 + grp, 128);
           turn_wait();
           turn_pass();
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_full[grp]);
+          __syncwarp();
         }
         mbar_wait(&o_full[grp], (n - 1) & 1);
+        __syncwarp();
         named_bar_sync(1 + grp, 128);
         continue;
       }
@@ -359,11 +376,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             q.y = pack_bf16x2(e[2], e[3]);
             q.z = pack_bf16x2(e[4], e[5]);
             q.w = pack_bf16x2(e[6], e[7]);
-            *reinterpret_cast<uint4*>(prow + ((c ^ rx) << 4)) = q;
+            if constexpr (FEAT & AF_PTMEM) tmem_st4(tP + 4 * c, q);
+            else *reinterpret_cast<uint4*>(prow + ((c ^ rx) << 4)) = q;
           }
           turn_pass();
           l += rs;
-          fence_proxy_async_smem();
+          if constexpr (FEAT & AF_PTMEM) tmem_st_wait();
+          else fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_full[grp]);
@@ -435,12 +454,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         // ---- P = exp2(S*c - m_used) -> bf16, 128B-swizzled K-major tile in this group's P buffer ----
         float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+        [[maybe_unused]] uint32_t pk[32];
         turn_wait();
 #pragma unroll
         for (int c = 0; c < 16; ++c) {  // 16-byte chunks of 8 keys
           float e[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(s[8 * c + i]), p.scale_log2, -m_used));
+          for (int i = 0; i < 8; ++i) {
+            const float x = fmaf(__uint_as_float(s[8 * c + i]), p.scale_log2, -m_used);
+            e[i] = ((FEAT & AF_EMU) && (i == 3 || i == 7)) ? ex2_fma(x) : ex2_approx(x);
+          }
           if constexpr (!(FEAT & AF_ONES)) {
             rs0 += e[0] + e[4];
             rs1 += e[1] + e[5];
@@ -452,11 +475,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           q.y = pack_bf16x2(e[2], e[3]);
           q.z = pack_bf16x2(e[4], e[5]);
           q.w = pack_bf16x2(e[6], e[7]);
-          *reinterpret_cast<uint4*>(prow + (c >> 3) * TILE_BYTES + (((c & 7) ^ rx) << 4)) = q;
+          if constexpr (FEAT & AF_PTMEM) {
+            // packed probabilities of 64 keys are collected in 32 registers and leave with one tcgen05.st
+            pk[4 * (c & 7) + 0] = q.x; pk[4 * (c & 7) + 1] = q.y; pk[4 * (c & 7) + 2] = q.z; pk[4 * (c & 7) + 3] = q.w;
+            if ((c & 7) == 7) tmem_st32(tP + 32 * (c >> 3), pk);
+          } else {
+            *reinterpret_cast<uint4*>(prow + (c >> 3) * TILE_BYTES + (((c & 7) ^ rx) << 4)) = q;
+          }
         }
         turn_pass();
         l += (rs0 + rs1) + (rs2 + rs3);
-        fence_proxy_async_smem();
+        if constexpr (FEAT & AF_PTMEM) tmem_st_wait();
+        else fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[grp]);
@@ -737,8 +767,12 @@ int make_qkv_map(CUtensorMap* m, const bf16* base, long long ld, int ntok, int b
 
 }  // namespace
 
-// default feature set (from the same-box A/B measurements in profiles/r02_attn_ab_*.log)
-constexpr int kDefaultFeat = AF_SKIP;
+// Default feature set, from the same-box A/B measurements in profiles/r02_attn_ab_*.log (stand-alone, n = 768 / 769):
+// round-1 kernel 586 / 405 TF/s; AF_PTMEM 647 / 453 (+10 %); AF_SKIP +1.7 % at n = 769 only (and compute-sanitizer's
+// synccheck objects to the ping-pong named barrier being reached from the dead-warp skeleton's own call site, so it stays
+// opt-in); AF_ONES +-0; AF_EMU -6 %; no ping-pong -14 %.  Variants that were built, measured and removed again (git history,
+// logs under profiles/): a two-pass register-light softmax (-15 %), two threads per query row at 96 registers (-45 %, spills).
+constexpr int kDefaultFeat = AF_PTMEM;
 
 int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   STA_REQUIRE(a.batch > 0 && a.heads > 0 && a.nq > 0 && a.nk > 0, "empty attention problem");
@@ -812,6 +846,9 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   STA_ATTN_CASE(AF_SKIP)
   STA_ATTN_CASE(AF_ONES)
   STA_ATTN_CASE(AF_SKIP | AF_ONES)
+  STA_ATTN_CASE(AF_PTMEM)
+  STA_ATTN_CASE(AF_SKIP | AF_PTMEM)
+  STA_ATTN_CASE(AF_SKIP | AF_PTMEM | AF_EMU)
 #undef STA_ATTN_CASE
   set_last_error("launch_attention: no kernel instance for this STA_ATTN_FEAT value");
   return 2;

@@ -912,8 +912,9 @@ int check_ready(StaModel* m) {
   return 0;
 }
 
-// DPT parts per view in the host entry point: the tile counts of the head convolutions stay >> 148 down to 4 images per part
-int host_dpt_parts(int B) { return B >= 8 ? StaModel::kMaxParts : (B >= 2 ? 2 : 1); }
+// DPT parts per view in the host entry point.  Two halves measured best on B200 (r02: exposed copy 2.0 ms per 16-pair step;
+// four parts of 4 images shorten the D2H tail but the smaller DPT batches cost more than that: 3.0 ms).
+int host_dpt_parts(int B) { return B >= 2 ? 2 : 1; }
 
 int forward_chunk(const Ctx& c, const void* img1, const void* img2, int img_is_bf16, int B, int H, int W,
                   float* pts3d, float* conf, float* pose, float* pose_conf, int B_total,
@@ -946,7 +947,7 @@ int forward_chunk(const Ctx& c, const void* img1, const void* img2, int img_is_b
   }
   // DPT heads: view 1 images then view 2 images (outputs are [2][B_total] blocks).  The host entry point passes events:
   // each view is then processed in `halves` parts (host_dpt_parts) and an event is recorded after every part, so that the
-  // D2H copy of one part runs under the head of the next and only the last part of the outputs (1/8 at B >= 8) is exposed.
+  // D2H copy of one part runs under the head of the next and only the last quarter of the outputs is exposed.
   const long long px = static_cast<long long>(H) * W;
   const int halves = ev_parts ? host_dpt_parts(B) : 1;
   for (int v = 0; v < 2; ++v) {
