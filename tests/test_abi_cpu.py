@@ -78,4 +78,7 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
-                assert "oracle" not in src.replace("oracle/", "").lower() or f == "sta_model.py" and False, (dp, f)
+                # no import of, and no path into, the oracle package; the word may only appear in comments that point at
+                # oracle/<file> as the checker of a kernel
+                assert "import oracle" not in src and "from oracle" not in src, (dp, f)
+                assert "oracle" not in src.replace("oracle/", "").lower(), (dp, f)

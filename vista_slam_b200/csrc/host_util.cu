@@ -1,5 +1,8 @@
 #include "host_util.h"
 
+#include <stdlib.h>
+
+#include <atomic>
 #include <mutex>
 
 namespace sta {

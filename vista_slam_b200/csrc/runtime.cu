@@ -208,6 +208,11 @@ struct StaModel {
   int64_t launches = 0;
   int max_pairs_per_chunk = 16;
   int rp_K = 0, rp_H = 0, rp_W = 0;  // state between sta_regress_pairs_begin and _finish
+  // The handle owns ONE workspace / io buffer / graph set: calls are ordered on whatever stream they are given.  When the
+  // caller switches streams, the new stream first waits for the work this handle enqueued on the previous one.
+  cudaStream_t last_stream = nullptr;
+  bool has_last_stream = false;
+  cudaEvent_t ev_switch = nullptr;
 
   // ---- CUDA-graph replay of the launch-bound small-batch entry points (SLAM mode) ----
   struct GraphEntry {
@@ -916,6 +921,18 @@ int check_ready(StaModel* m) {
 // four parts of 4 images shorten the D2H tail but the smaller DPT batches cost more than that: 3.0 ms).
 int host_dpt_parts(int B) { return B >= 2 ? 2 : 1; }
 
+// one stream per handle at a time: order a call on `st` after everything this handle enqueued on its previous stream
+int enter_stream(StaModel* m, cudaStream_t st) {
+  if (m->has_last_stream && m->last_stream != st) {
+    if (!m->ev_switch) STA_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_switch, cudaEventDisableTiming));
+    STA_CHECK_CUDA(cudaEventRecord(m->ev_switch, m->last_stream));
+    STA_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_switch, 0));
+  }
+  m->last_stream = st;
+  m->has_last_stream = true;
+  return 0;
+}
+
 int forward_chunk(const Ctx& c, const void* img1, const void* img2, int img_is_bf16, int B, int H, int W,
                   float* pts3d, float* conf, float* pose, float* pose_conf, int B_total,
                   cudaEvent_t* ev_parts = nullptr) {
@@ -1039,6 +1056,7 @@ void sta_destroy(StaModel* m) {
   if (m->splitk_ws) cudaFree(m->splitk_ws);
   drop_graphs(m);
   if (m->s_cap) cudaStreamDestroy(m->s_cap);
+  if (m->ev_switch) cudaEventDestroy(m->ev_switch);
   if (m->s_in) {
     cudaStreamDestroy(m->s_in);
     cudaStreamDestroy(m->s_out);
@@ -1189,6 +1207,7 @@ int sta_encode(StaModel* m, const void* img_dev, int img_is_bf16, int B, int H, 
   STA_REQUIRE(B > 0 && H % 16 == 0 && W % 16 == 0 && H > 0 && W > 0, "image size must be a positive multiple of 16");
   STA_REQUIRE(H / 16 <= 1024 && W / 16 <= 1024, "token grid exceeds the RoPE table");
   Ctx c{m, static_cast<cudaStream_t>(stream)};
+  RUN(enter_stream(m, c.st));
   const int h = H / 16, w = W / 16, N = h * w;
   RUN(ensure_ws(m, B, h, w));
   EncBufs e = take_enc(m->ws, B, N);
@@ -1225,6 +1244,7 @@ int sta_decode(StaModel* m, const float* feat1_dev, const float* feat2_dev, cons
   RUN(check_ready(m));
   STA_REQUIRE(B > 0 && N > 0, "empty batch");
   Ctx c{m, static_cast<cudaStream_t>(stream)};
+  RUN(enter_stream(m, c.st));
   // workspace sized as an (N x 1) token grid: only token counts matter for the decoder buffers
   RUN(ensure_ws(m, 2 * B, N, 1));
   DecBufs d = take_dec(m->ws, 2 * B, N);
@@ -1254,6 +1274,7 @@ int sta_head_pts(StaModel* m, const float* enc_feat_dev, const float* dec6_dev, 
   RUN(check_ready(m));
   STA_REQUIRE(B > 0 && H % 16 == 0 && W % 16 == 0, "image size must be a multiple of 16");
   Ctx c{m, static_cast<cudaStream_t>(stream)};
+  RUN(enter_stream(m, c.st));
   const int h = H / 16, w = W / 16, N = h * w;
   RUN(ensure_ws(m, B, h, w));
   Workspace& ws = m->ws;
@@ -1282,6 +1303,7 @@ int sta_regress_pairs(StaModel* m, const float* feat_i_dev, const float* feat_j_
   STA_REQUIRE(feat_i_dev && feat_j_dev && pose_out_dev && pose_conf_out_dev && pts3d_out_dev && conf_out_dev,
               "null pointer");
   Ctx c{m, static_cast<cudaStream_t>(stream)};
+  RUN(enter_stream(m, c.st));
   const int h = H / 16, w = W / 16, N = h * w, S = 2 * K, M = N + 1;
   RUN(ensure_ws(m, S, h, w));
   Workspace& ws = m->ws;
@@ -1368,6 +1390,7 @@ int sta_regress_pairs_begin(StaModel* m, const float* feat_i_dev, const float* f
   STA_REQUIRE(H / 16 <= 1024 && W / 16 <= 1024, "token grid exceeds the RoPE table");
   STA_REQUIRE(feat_i_dev && feat_j_dev && pose_out_dev && pose_conf_out_dev, "null pointer");
   Ctx c{m, static_cast<cudaStream_t>(stream)};
+  RUN(enter_stream(m, c.st));
   const int h = H / 16, w = W / 16, N = h * w, S = 2 * K, M = N + 1;
   RUN(ensure_ws(m, S, h, w));
   Workspace& ws = m->ws;
@@ -1411,6 +1434,7 @@ int sta_regress_pairs_finish(StaModel* m, const int* edge_idx_host, int n_sel, f
   const bool consumers = intri_out_dev || depth_out_dev || conf_mean_out_dev;
   if (consumers) STA_REQUIRE(scratch != nullptr && intri_out_dev != nullptr, "the pointmap consumers need scratch and intri_out");
   Ctx c{m, static_cast<cudaStream_t>(stream)};
+  RUN(enter_stream(m, c.st));
   const int h = H / 16, w = W / 16, N = h * w, S = 2 * K, S2 = 2 * n_sel;
   RUN(ensure_ws(m, S, h, w));  // same shape as phase 1: no reallocation, and the same take sequence gives the same buffers
   Workspace& ws = m->ws;
@@ -1479,6 +1503,7 @@ int sta_forward_pairs(StaModel* m, const void* img1_dev, const void* img2_dev, i
   STA_REQUIRE(B > 0 && H % 16 == 0 && W % 16 == 0 && H > 0 && W > 0, "image size must be a positive multiple of 16");
   STA_REQUIRE(H / 16 <= 1024 && W / 16 <= 1024, "token grid exceeds the RoPE table");
   Ctx c{m, static_cast<cudaStream_t>(stream)};
+  RUN(enter_stream(m, c.st));
   const size_t esz = img_is_bf16 ? 2 : 4;
   const long long px = static_cast<long long>(H) * W;
   for (int b0 = 0; b0 < B; b0 += m->max_pairs_per_chunk) {
@@ -1499,6 +1524,7 @@ int sta_forward_pairs_host(StaModel* m, const void* img1_host, const void* img2_
   STA_REQUIRE(B > 0 && H % 16 == 0 && W % 16 == 0 && H > 0 && W > 0, "image size must be a positive multiple of 16");
   STA_REQUIRE(H / 16 <= 1024 && W / 16 <= 1024, "token grid exceeds the RoPE table");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RUN(enter_stream(m, st));
   const size_t esz = img_is_bf16 ? 2 : 4;
   const size_t px = static_cast<size_t>(H) * W;
   const size_t img_bytes = static_cast<size_t>(B) * 3 * px * esz;

@@ -243,10 +243,15 @@ class SymmetricTwoViewAssociation(nn.Module):
         with torch.cuda.device(like.device):
             if self._handle is None:
                 self._handle = self._create(L)
+            # sta_load_tensor packs on the legacy default stream: make sure dtype conversions / copies issued on the
+            # current (possibly non-blocking) torch stream have landed before the library reads the tensors
+            torch.cuda.current_stream().synchronize()
             for name, t in self.state_dict().items():
                 src = t.detach()
                 on_dev = 1 if src.is_cuda else 0
                 src = src.to(torch.float32).contiguous()
+                if on_dev and src.data_ptr() != t.data_ptr():
+                    torch.cuda.current_stream().synchronize()  # a conversion kernel was just enqueued on the torch stream
                 shape = (ctypes.c_int64 * src.dim())(*src.shape)
                 _lib.check(L.sta_load_tensor(self._handle, name.encode(), _lib.ptr(src), shape, src.dim(), on_dev),
                            "sta_load_tensor(%s)" % name)
