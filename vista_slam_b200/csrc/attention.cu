@@ -58,7 +58,8 @@ static_assert(ATT_SMEM <= 227 * 1024, "attention shared memory");
 //            bound otherwise: ~64 clk instead of 32), and the softmax needs no st.shared / fence.proxy.async.
 //            TMEM: S 2 x 128 | O 2 x 64 | P 2 x 64 = 512 columns (hence exclusive with AF_ONES).
 //   AF_EMU   2 of every 8 exponentials on the FMA pipe (ex2_fma, degree-3 polynomial) instead of the 16-lane/clk MUFU.
-enum AttnFeat : int { AF_SKIP = 1, AF_ONES = 8, AF_PTMEM = 16, AF_EMU = 32 };
+//   AF_1Q    one query tile per CTA, two CTAs per SM (attention_1q_kernel below; implies P in tensor memory).
+enum AttnFeat : int { AF_SKIP = 1, AF_ONES = 8, AF_PTMEM = 16, AF_EMU = 32, AF_1Q = 64 };
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 struct AttnParams {
@@ -537,6 +538,363 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }
 
 // ---------------------------------------------------------------------------
+// AF_1Q: the same pipeline with ONE 128-query tile per CTA and TWO CTAs per SM (256 threads, 112 KB of shared memory and 256
+// TMEM columns each: S 128 | O 64 | P 64).  The two query tiles that share an SM are then driven by two independent
+// MMA-issuing threads (in the pair kernel one in-order thread serves both softmax groups), work items are single tiles (the
+// decoder's 769 rows cost 7 tiles, not 4 pairs = 8), and the co-resident CTAs drift apart by themselves, so one CTA's exp2
+// phase overlaps the other's TMEM load / row maximum / handshakes without named-barrier ping-pong.  K / V tiles are loaded
+// once per CTA (twice per SM): L2 -> shared-memory traffic is not what bounds this kernel.
+// setmaxnreg: 128 registers per thread at launch (2 x 256 threads per SM), warps 0-3 shrink to 40, the softmax warpgroup
+// grows to 216 -- exactly the file.
+// ---------------------------------------------------------------------------
+constexpr int ATT1_THREADS = 256;
+constexpr int KV1_STAGES = 2;
+constexpr uint32_t ATT1_OFF_K = 2 * TILE_BYTES;                         // Q x2 | K x2 | V x2 | O staging | barriers
+constexpr uint32_t ATT1_OFF_V = ATT1_OFF_K + KV1_STAGES * TILE_BYTES;
+constexpr uint32_t ATT1_OFF_O = ATT1_OFF_V + KV1_STAGES * TILE_BYTES;
+constexpr uint32_t ATT1_OFF_BAR = ATT1_OFF_O + TILE_BYTES;
+constexpr uint32_t ATT1_SMEM = ATT1_OFF_BAR + 256;
+static_assert(2 * (ATT1_SMEM + 1024) <= 228 * 1024, "two attention CTAs per SM");
+
+__global__ void __launch_bounds__(ATT1_THREADS, 2)
+attention_1q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p,
+                    int q_col0, int k_col0, int v_col0) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;  // buffer b at sQ + b * TILE_BYTES
+  uint8_t* sK = smem + ATT1_OFF_K;
+  uint8_t* sV = smem + ATT1_OFF_V;
+  uint8_t* sO = smem + ATT1_OFF_O;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT1_OFF_BAR);
+  uint64_t* q_full = bars + 0;   // [2]
+  uint64_t* q_empty = bars + 2;  // [2]
+  uint64_t* k_full = bars + 4;   // [2]
+  uint64_t* k_empty = bars + 6;  // [2]
+  uint64_t* v_full = bars + 8;   // [2]
+  uint64_t* v_empty = bars + 10; // [2]
+  uint64_t* s_full = bars + 12;  // MMA -> softmax: S ready
+  uint64_t* s_free = bars + 13;  // softmax -> MMA: S is in registers
+  uint64_t* p_full = bars + 14;  // softmax -> MMA: P written to TMEM (and O rescaled if needed)
+  uint64_t* o_full = bars + 15;  // MMA -> softmax: O += P V done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int T = (p.nk + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) device_fatal("dynamic shared memory is not 1024-byte aligned");
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 4);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;  // columns: S [0,128) O [128,192) P [192,256)
+  pdl_wait();
+  pdl_launch_dependents();
+
+  const int qtiles = (p.nq - p.q_row0 + 127) / 128;
+  const int nitems = qtiles * p.heads * p.batch;
+  auto decode = [&](int w, int& q0, int& head, int& b, int& kvb) {
+    const int qt = w % qtiles;  // query tile fastest: the tiles of one (sample, head) run side by side and share K / V in L2
+    const int rest = w / qtiles;
+    head = rest % p.heads;
+    b = rest / p.heads;
+    q0 = p.q_row0 + qt * 128;
+    kvb = (b + p.kv_batch_shift) % p.batch;
+  };
+  const int my_items = (nitems > static_cast<int>(blockIdx.x))
+                           ? (nitems - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
+                           : 0;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (elect_one()) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        int st = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < my_items; ++it) {
+          int q0, head, b, kvb;
+          decode(static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x), q0, head, b, kvb);
+          const int qb = it & 1;
+          mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[qb], TILE_BYTES);
+          tma_load_3d(sQ + qb * TILE_BYTES, &tmQ, &q_full[qb], q_col0 + head * 64, q0, b);
+          for (int j = 0; j < T; ++j) {
+            mbar_wait(&k_empty[st], ph ^ 1);
+            mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+            tma_load_3d(sK + st * TILE_BYTES, &tmK, &k_full[st], k_col0 + head * 64, j * 128, kvb);
+            mbar_wait(&v_empty[st], ph ^ 1);
+            mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+            tma_load_3d(sV + st * TILE_BYTES, &tmV, &v_full[st], v_col0 + head * 64, j * 128, kvb);
+            if (++st == KV1_STAGES) { st = 0; ph ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (elect_one()) {
+        constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc_s16 = make_idesc_bf16(128, 16, 0, 0);  // narrow tail tile (<= 16 valid keys)
+        constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);    // B (= V) is MN-major
+        const bool narrow_tail = (p.nk - (T - 1) * 128) <= 16;
+        const int total = my_items * T;
+        int s_it = 0, s_j = 0, s_st = 0;
+        uint32_t s_ph = 0;
+        auto issue_s = [&]() {
+          const int qi = s_it & 1;
+          if (s_j == 0) mbar_wait(&q_full[qi], (s_it >> 1) & 1);
+          mbar_wait(&k_full[s_st], s_ph);
+          tc_fence_after();
+          const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + qi * TILE_BYTES));
+          const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + s_st * TILE_BYTES));
+          const uint32_t ids = (narrow_tail && s_j == T - 1) ? idesc_s16 : idesc_s;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, qdesc + 2 * k, kdesc + 2 * k, ids, k != 0);
+          umma_commit(&k_empty[s_st]);
+          if (s_j == T - 1) umma_commit(&q_empty[qi]);
+          umma_commit(s_full);
+          if (++s_st == KV1_STAGES) { s_st = 0; s_ph ^= 1; }
+          if (++s_j == T) { s_j = 0; ++s_it; }
+        };
+        if (total > 0) issue_s();
+        int v_st = 0, j = 0;
+        uint32_t v_ph = 0;
+        for (int n = 0; n < total; ++n) {
+          if (n + 1 < total) {  // S(n+1) as soon as the softmax threads hold S(n) in registers
+            mbar_wait(s_free, n & 1);
+            issue_s();
+          }
+          mbar_wait(p_full, n & 1);
+          mbar_wait(&v_full[v_st], v_ph);
+          tc_fence_after();
+          const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + v_st * TILE_BYTES));
+          const int ksteps = (narrow_tail && j == T - 1) ? 1 : 8;
+          for (int k = 0; k < ksteps; ++k)  // A = P from tensor memory (8 packed columns per 16 keys), B = V (MN-major)
+            umma_bf16_ts(tmem_base + 128, tmem_base + 192 + 8 * k, vdesc + (2048 >> 4) * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&v_empty[v_st]);
+          umma_commit(o_full);
+          if (++v_st == KV1_STAGES) { v_st = 0; v_ph ^= 1; }
+          if (++j == T) j = 0;
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
+    // ===================== softmax warpgroup: one thread per query row =====================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const int rx = r & 7;
+    const uint32_t tS = tmem_base + lane_addr;
+    const uint32_t tO = tmem_base + lane_addr + 128;
+    const uint32_t tP = tmem_base + lane_addr + 192;
+    uint8_t* orow = sO + r * 128;
+    const bool store_thr = warp == 4 && lane == 0;
+    int n = 0;
+    for (int it = 0; it < my_items; ++it) {
+      int q0, head, b, kvb;
+      decode(static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x), q0, head, b, kvb);
+      float m_used = -INFINITY;
+      float l = 0.f;
+      for (int j = 0; j < T; ++j, ++n) {
+        const int nvalid = p.nk - j * 128;  // >= 1
+        mbar_wait(s_full, n & 1);
+        tc_fence_after();
+        if (nvalid <= 16 && j == T - 1) {
+          // ---- narrow tail tile: S is 128 x 16, P V uses a single 16-key step ----
+          uint32_t s16[16];
+          tmem_ld16(tS, s16);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free);
+          float mxn = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (i >= nvalid) s16[i] = 0xff800000u;
+            mxn = fmaxf(mxn, __uint_as_float(s16[i]));
+          }
+          const float m_true = mxn * p.scale_log2;
+          const bool raise = m_true > m_used + kRescaleThreshold;
+          const float m_new = raise ? m_true : m_used;
+          const float factor = raise ? ex2_approx(m_used - m_new) : 1.0f;
+          l *= factor;
+          m_used = m_new;
+          if (j > 0) {
+            mbar_wait(o_full, (n - 1) & 1);
+            if (__any_sync(0xffffffffu, raise)) {
+              tc_fence_after();
+#pragma unroll
+              for (int c = 0; c < 64; c += 32) {
+                uint32_t o[32];
+                tmem_ld32(tO + c, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                tmem_st32(tO + c, o);
+              }
+            }
+          }
+          float rs = 0.f;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              e[i] = ex2_approx(fmaf(__uint_as_float(s16[8 * c + i]), p.scale_log2, -m_used));
+              rs += e[i];
+            }
+            tmem_st4(tP + 4 * c, make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]),
+                                            pack_bf16x2(e[6], e[7])));
+          }
+          l += rs;
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full);
+          continue;
+        }
+        // ---- the whole score row into registers; release the S buffer for the next Q K^T ----
+        uint32_t s[128];
+        {
+          uint32_t (&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+          uint32_t (&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+          uint32_t (&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+          uint32_t (&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+          tmem_ld32(tS, s0);
+          tmem_ld32(tS + 32, s1);
+          tmem_ld32(tS + 64, s2);
+          tmem_ld32(tS + 96, s3);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+        if (nvalid < 128) {  // ragged last key tile: masked scores contribute exp2(-inf) = 0
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= nvalid) s[i] = 0xff800000u;
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+        }
+        const float m_true = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+        // lazy rescaling: keep the old reference maximum unless the row maximum grew by more than 2^8
+        const bool raise = m_true > m_used + kRescaleThreshold;  // always true on the first tile (m_used = -inf)
+        const float m_new = raise ? m_true : m_used;
+        const float factor = raise ? ex2_approx(m_used - m_new) : 1.0f;  // first tile: exp2(-inf) = 0
+        l *= factor;
+        m_used = m_new;
+        // the previous P V must be complete before P is overwritten (and before O is rescaled)
+        if (j > 0) {
+          mbar_wait(o_full, (n - 1) & 1);
+          if (__any_sync(0xffffffffu, raise)) {
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+              uint32_t o[32];
+              tmem_ld32(tO + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+              tmem_st32(tO + c, o);
+            }
+          }
+        }
+        // ---- P = exp2(S*c - m_used) -> packed bf16 -> tensor memory (64 keys per tcgen05.st) ----
+        float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(s[8 * c + i]), p.scale_log2, -m_used));
+          rs0 += e[0] + e[4];
+          rs1 += e[1] + e[5];
+          rs2 += e[2] + e[6];
+          rs3 += e[3] + e[7];
+          pk[4 * (c & 7) + 0] = pack_bf16x2(e[0], e[1]);
+          pk[4 * (c & 7) + 1] = pack_bf16x2(e[2], e[3]);
+          pk[4 * (c & 7) + 2] = pack_bf16x2(e[4], e[5]);
+          pk[4 * (c & 7) + 3] = pack_bf16x2(e[6], e[7]);
+          if ((c & 7) == 7) tmem_st32(tP + 32 * (c >> 3), pk);
+        }
+        l += (rs0 + rs1) + (rs2 + rs3);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      // ---- item epilogue: O / l -> bf16 -> 128B-swizzled staging tile -> one TMA store ----
+      mbar_wait(o_full, (n - 1) & 1);
+      tc_fence_after();
+      if (it > 0) {  // the previous item's TMA store must have finished reading the staging tile
+        if (store_thr) tma_store_wait_read();
+        named_bar_sync(1, 128);
+      }
+      const float inv_l = 1.0f / l;
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t o[32];
+        tmem_ld32(tO + c, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jc = 0; jc < 4; ++jc) {
+          uint4 q;
+          q.x = pack_bf16x2(__uint_as_float(o[8 * jc + 0]) * inv_l, __uint_as_float(o[8 * jc + 1]) * inv_l);
+          q.y = pack_bf16x2(__uint_as_float(o[8 * jc + 2]) * inv_l, __uint_as_float(o[8 * jc + 3]) * inv_l);
+          q.z = pack_bf16x2(__uint_as_float(o[8 * jc + 4]) * inv_l, __uint_as_float(o[8 * jc + 5]) * inv_l);
+          q.w = pack_bf16x2(__uint_as_float(o[8 * jc + 6]) * inv_l, __uint_as_float(o[8 * jc + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + ((((c >> 3) + jc) ^ rx) << 4)) = q;
+        }
+      }
+      tc_fence_before();  // the next item's first P V overwrites O only after p_full, i.e. after these loads
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (store_thr) {
+        tma_store_3d(&tmO, sO, head * 64, q0, b);  // rows >= nq are clipped by the TMA unit
+        tma_store_commit();
+      }
+    }
+    if (store_thr) tma_store_wait_all();
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Query row 0 of every (sample, head) -- the decoder's pose token -- against all nk keys.
 // One CTA (256 threads) per (head, sample): scores -> shared memory, block max / sum, then P V with 16-byte
 // loads.  ~1e-4 of the attention FLOPs but latency-bound: the loads are batched so that the whole kernel is
@@ -821,7 +1179,15 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
                               a.ldk, a.k_col0, a.v, a.ldv, a.v_col0, a.out, a.ldo, a.nq, a.nk, a.batch, a.kv_batch_shift,
                               p.scale_log2));
   }
-  const int feat = feat_env >= 0 ? feat_env : kDefaultFeat;
+  int feat = feat_env >= 0 ? feat_env : kDefaultFeat;
+  if (feat_env < 0) {
+    // One query tile per CTA (attention_1q_kernel) when the pair kernel would waste work: an odd number of query tiles (the
+    // decoder's 769 rows = 7 tiles: the 4th pair carries a dead tile; 525 vs 457 TF/s) or fewer pairs than SMs (SLAM mode:
+    // twice as many work items).  On full pairs the two kernels are equal (648 vs 653 TF/s) and the pair kernel loads K / V
+    // once per SM instead of twice.
+    const int qtiles = (a.nq - split + 127) / 128;
+    if ((qtiles & 1) || p.nitems < num_sms()) feat = AF_1Q;
+  }
   // Work items w = (query-tile pair fastest, head, sample) are dealt round-robin to the CTAs (w = blockIdx + it * grid), so
   // that neighbouring CTAs work on the pairs of ONE (sample, head) at the same time and share its K / V tiles in L2.  The
   // last pair of a 128k+1-row problem (the decoder's 769 rows) is much cheaper than the others (AF_SKIP): the grid is made
@@ -850,6 +1216,17 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   STA_ATTN_CASE(AF_SKIP | AF_PTMEM)
   STA_ATTN_CASE(AF_SKIP | AF_PTMEM | AF_EMU)
 #undef STA_ATTN_CASE
+  if (feat == AF_1Q) {
+    static PerDeviceOnce once;
+    STA_CHECK_CUDA(once.run([&] {
+      return cudaFuncSetAttribute(attention_1q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT1_SMEM);
+    }));
+    const int items1 = ((a.nq - split + 127) / 128) * a.heads * a.batch;
+    const int grid1 = items1 < 2 * num_sms() ? items1 : 2 * num_sms();
+    STA_CHECK_CUDA(launch_pdl(attention_1q_kernel, dim3(grid1), dim3(ATT1_THREADS), ATT1_SMEM, stream, 1, tmQ, tmK, tmV, tmO, p,
+                              a.q_col0, a.k_col0, a.v_col0));
+    return 0;
+  }
   set_last_error("launch_attention: no kernel instance for this STA_ATTN_FEAT value");
   return 2;
 }

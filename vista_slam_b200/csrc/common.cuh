@@ -340,6 +340,20 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
   d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
   return d;
 }
+// Same layout with an arbitrary stride between the 8-row groups and a start address that is only 128-byte (one row)
+// aligned: bits [49,52) carry the "matrix base offset" = (start >> 7) & 7, the phase of the 128-byte swizzle pattern at
+// the start row (PTX ISA, tcgen05 shared-memory descriptor).  Used by the halo-staged 3x3 convolution, whose nine filter
+// taps are nine row-shifted views of ONE staged input tile.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_ex(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>((saddr >> 7) & 7) << 49;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor: bf16 A/B, fp32 accumulate, M x N tile.
 // bits [4,6) c_format=1(f32) | [7,10) a_format=1(bf16) | [10,13) b_format=1(bf16) | 15 a_major | 16 b_major
 //      [17,23) N>>3 | [24,29) M>>4
