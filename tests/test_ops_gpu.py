@@ -90,3 +90,24 @@ def test_error_reporting_through_the_abi():
     d = bu.gemm_desc(epi=EPI_BF16, A=A, lda=64, W=A, ldw=64, M=128, N=48, K=64, out=A, ldo=48)  # N % 32 != 0
     rc = lib().sta_op_gemm(ctypes.byref(d), None)
     assert rc != 0 and b"multiple of 32" in lib().sta_last_error()
+
+
+@pytest.mark.parametrize("env,group", [
+    ({"STA_CONV_HALO": "0"}, "conv"),        # one TMA box per filter tap instead of the halo-staged tile
+    ({"STA_CONV_EW16": "0"}, "conv"),        # 8 epilogue warps for the skip-tensor convolutions
+    ({"STA_ATTN_FEAT": "144"}, "attention"),  # query-tile-pair kernel for every shape
+    ({"STA_ATTN_FEAT": "192"}, "attention"),  # one-query-tile-per-CTA kernel for every shape
+    ({"STA_ATTN_FEAT": "16"}, "attention"),   # scalar FFMA / FADD softmax (A/B reference of the packed fp32 form)
+])
+def test_alternate_kernel_routes(env, group):
+    """The launchers pick one kernel variant per shape; the variants they do NOT pick by default (kept for same-box A/B
+    timing) must stay correct too.  The knobs are read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "bringup.py"), group], env=dict(os.environ, **env),
+                       capture_output=True, text=True, timeout=600)
+    lines = [l for l in r.stdout.splitlines() if l.strip().endswith(("PASS", "FAIL"))]
+    assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-2000:]
+    assert not [l for l in lines if l.endswith("FAIL")], r.stdout[-3000:]

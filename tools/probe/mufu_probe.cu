@@ -66,6 +66,33 @@ __global__ void probe(float* out, long long* clk, int iters, float scale, float 
         }
       }
       m += 1e-7f;
+    } else if (MODE == 8) {  // packed fp32: FFMA2 for the scale-subtract, FADD2 for the row sums
+      const float2 sc2 = make_float2(scale, scale), nm2 = make_float2(-m, -m);
+      const uint64_t scp = *reinterpret_cast<const uint64_t*>(&sc2), nmp = *reinterpret_cast<const uint64_t*>(&nm2);
+      uint64_t a01 = 0, a23 = 0;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const float2 sv = make_float2(s[8 * c + i], s[8 * c + i + 1]);
+          uint64_t t;
+          asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t) : "l"(*reinterpret_cast<const uint64_t*>(&sv)), "l"(scp), "l"(nmp));
+          const float2 tv = *reinterpret_cast<float2*>(&t);
+          e[i] = ex2(tv.x);
+          e[i + 1] = ex2(tv.y);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i += 4) {
+          const float2 p0 = make_float2(e[i], e[i + 1]), p1 = make_float2(e[i + 2], e[i + 3]);
+          asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a01) : "l"(*reinterpret_cast<const uint64_t*>(&p0)));
+          asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a23) : "l"(*reinterpret_cast<const uint64_t*>(&p1)));
+        }
+        x ^= pack(e[0], e[1]) ^ pack(e[2], e[3]) ^ pack(e[4], e[5]) ^ pack(e[6], e[7]);
+      }
+      const float2 r01 = *reinterpret_cast<float2*>(&a01), r23 = *reinterpret_cast<float2*>(&a23);
+      acc0 += r01.x; acc1 += r01.y; acc2 += r23.x; acc3 += r23.y;
+      m += 1e-7f;
     } else if (MODE == 4) {  // 3/4 MUFU + 1/4 polynomial on the FMA pipe, mix as MODE 1
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
@@ -125,6 +152,7 @@ int main() {
     run<5>("ffma + ex2 + pack (no row sum)", t, 1.f);
     run<6>("ffma + ex2 + rowsum + prmt", t, 1.f);
     run<7>("ffma + ex2 + prmt", t, 1.f);
+    run<8>("ffma2 + ex2 + fadd2 rowsum + pack", t, 1.f);
   }
   return 0;
 }

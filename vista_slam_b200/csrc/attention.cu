@@ -59,7 +59,8 @@ static_assert(ATT_SMEM <= 227 * 1024, "attention shared memory");
 //            TMEM: S 2 x 128 | O 2 x 64 | P 2 x 64 = 512 columns (hence exclusive with AF_ONES).
 //   AF_EMU   2 of every 8 exponentials on the FMA pipe (ex2_fma, degree-3 polynomial) instead of the 16-lane/clk MUFU.
 //   AF_1Q    one query tile per CTA, two CTAs per SM (attention_1q_kernel below; implies P in tensor memory).
-enum AttnFeat : int { AF_SKIP = 1, AF_ONES = 8, AF_PTMEM = 16, AF_EMU = 32, AF_1Q = 64 };
+//   AF_X2    scale-subtract and row sums with the packed fp32 instructions FFMA2 / FADD2 (common.cuh::f32x2_*).
+enum AttnFeat : int { AF_SKIP = 1, AF_ONES = 8, AF_PTMEM = 16, AF_EMU = 32, AF_1Q = 64, AF_X2 = 128 };
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 struct AttnParams {
@@ -455,11 +456,28 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         // ---- P = exp2(S*c - m_used) -> bf16, 128B-swizzled K-major tile in this group's P buffer ----
         float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+        [[maybe_unused]] uint64_t rsA = 0, rsB = 0;  // AF_X2: two packed pairs of row-sum partials
+        [[maybe_unused]] const uint64_t sc2 = f32x2_pack(p.scale_log2, p.scale_log2), nm2 = f32x2_pack(-m_used, -m_used);
         [[maybe_unused]] uint32_t pk[32];
         turn_wait();
 #pragma unroll
         for (int c = 0; c < 16; ++c) {  // 16-byte chunks of 8 keys
           float e[8];
+          if constexpr (FEAT & AF_X2) {
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              float t0, t1;
+              f32x2_unpack(f32x2_fma(f32x2_pack(__uint_as_float(s[8 * c + i]), __uint_as_float(s[8 * c + i + 1])), sc2, nm2), t0, t1);
+              e[i] = ex2_approx(t0);
+              e[i + 1] = ex2_approx(t1);
+            }
+            if constexpr (!(FEAT & AF_ONES)) {
+              rsA = f32x2_add(rsA, f32x2_pack(e[0], e[1]));
+              rsB = f32x2_add(rsB, f32x2_pack(e[2], e[3]));
+              rsA = f32x2_add(rsA, f32x2_pack(e[4], e[5]));
+              rsB = f32x2_add(rsB, f32x2_pack(e[6], e[7]));
+            }
+          } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float x = fmaf(__uint_as_float(s[8 * c + i]), p.scale_log2, -m_used);
@@ -470,6 +488,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             rs1 += e[1] + e[5];
             rs2 += e[2] + e[6];
             rs3 += e[3] + e[7];
+          }
           }
           uint4 q;
           q.x = pack_bf16x2(e[0], e[1]);
@@ -485,6 +504,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
         turn_pass();
+        if constexpr (FEAT & AF_X2) {
+          f32x2_unpack(rsA, rs0, rs1);
+          f32x2_unpack(rsB, rs2, rs3);
+        }
         l += (rs0 + rs1) + (rs2 + rs3);
         if constexpr (FEAT & AF_PTMEM) tmem_st_wait();
         else fence_proxy_async_smem();
@@ -556,6 +579,7 @@ constexpr uint32_t ATT1_OFF_BAR = ATT1_OFF_O + TILE_BYTES;
 constexpr uint32_t ATT1_SMEM = ATT1_OFF_BAR + 256;
 static_assert(2 * (ATT1_SMEM + 1024) <= 228 * 1024, "two attention CTAs per SM");
 
+template <bool X2>
 __global__ void __launch_bounds__(ATT1_THREADS, 2)
 attention_1q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p,
@@ -829,21 +853,41 @@ attention_1q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         // ---- P = exp2(S*c - m_used) -> packed bf16 -> tensor memory (64 keys per tcgen05.st) ----
         float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+        [[maybe_unused]] uint64_t rsA = 0, rsB = 0;  // X2: two packed pairs of row-sum partials
+        [[maybe_unused]] const uint64_t sc2 = f32x2_pack(p.scale_log2, p.scale_log2), nm2 = f32x2_pack(-m_used, -m_used);
         uint32_t pk[32];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           float e[8];
+          if constexpr (X2) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(s[8 * c + i]), p.scale_log2, -m_used));
-          rs0 += e[0] + e[4];
-          rs1 += e[1] + e[5];
-          rs2 += e[2] + e[6];
-          rs3 += e[3] + e[7];
+            for (int i = 0; i < 8; i += 2) {
+              float t0, t1;
+              f32x2_unpack(f32x2_fma(f32x2_pack(__uint_as_float(s[8 * c + i]), __uint_as_float(s[8 * c + i + 1])), sc2, nm2), t0, t1);
+              e[i] = ex2_approx(t0);
+              e[i + 1] = ex2_approx(t1);
+            }
+            rsA = f32x2_add(rsA, f32x2_pack(e[0], e[1]));
+            rsB = f32x2_add(rsB, f32x2_pack(e[2], e[3]));
+            rsA = f32x2_add(rsA, f32x2_pack(e[4], e[5]));
+            rsB = f32x2_add(rsB, f32x2_pack(e[6], e[7]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(s[8 * c + i]), p.scale_log2, -m_used));
+            rs0 += e[0] + e[4];
+            rs1 += e[1] + e[5];
+            rs2 += e[2] + e[6];
+            rs3 += e[3] + e[7];
+          }
           pk[4 * (c & 7) + 0] = pack_bf16x2(e[0], e[1]);
           pk[4 * (c & 7) + 1] = pack_bf16x2(e[2], e[3]);
           pk[4 * (c & 7) + 2] = pack_bf16x2(e[4], e[5]);
           pk[4 * (c & 7) + 3] = pack_bf16x2(e[6], e[7]);
           if ((c & 7) == 7) tmem_st32(tP + 32 * (c >> 3), pk);
+        }
+        if constexpr (X2) {
+          f32x2_unpack(rsA, rs0, rs1);
+          f32x2_unpack(rsB, rs2, rs3);
         }
         l += (rs0 + rs1) + (rs2 + rs3);
         tmem_st_wait();
@@ -1130,7 +1174,7 @@ int make_qkv_map(CUtensorMap* m, const bf16* base, long long ld, int ntok, int b
 // synccheck objects to the ping-pong named barrier being reached from the dead-warp skeleton's own call site, so it stays
 // opt-in); AF_ONES +-0; AF_EMU -6 %; no ping-pong -14 %.  Variants that were built, measured and removed again (git history,
 // logs under profiles/): a two-pass register-light softmax (-15 %), two threads per query row at 96 registers (-45 %, spills).
-constexpr int kDefaultFeat = AF_PTMEM;
+constexpr int kDefaultFeat = AF_PTMEM | AF_X2;
 
 int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   STA_REQUIRE(a.batch > 0 && a.heads > 0 && a.nq > 0 && a.nk > 0, "empty attention problem");
@@ -1186,7 +1230,7 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
     // twice as many work items).  On full pairs the two kernels are equal (648 vs 653 TF/s) and the pair kernel loads K / V
     // once per SM instead of twice.
     const int qtiles = (a.nq - split + 127) / 128;
-    if ((qtiles & 1) || p.nitems < num_sms()) feat = AF_1Q;
+    if ((qtiles & 1) || p.nitems < num_sms()) feat = AF_1Q | AF_X2;
   }
   // Work items w = (query-tile pair fastest, head, sample) are dealt round-robin to the CTAs (w = blockIdx + it * grid), so
   // that neighbouring CTAs work on the pairs of ONE (sample, head) at the same time and share its K / V tiles in L2.  The
@@ -1215,18 +1259,23 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   STA_ATTN_CASE(AF_PTMEM)
   STA_ATTN_CASE(AF_SKIP | AF_PTMEM)
   STA_ATTN_CASE(AF_SKIP | AF_PTMEM | AF_EMU)
+  STA_ATTN_CASE(AF_PTMEM | AF_X2)
 #undef STA_ATTN_CASE
-  if (feat == AF_1Q) {
-    static PerDeviceOnce once;
-    STA_CHECK_CUDA(once.run([&] {
-      return cudaFuncSetAttribute(attention_1q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT1_SMEM);
-    }));
-    const int items1 = ((a.nq - split + 127) / 128) * a.heads * a.batch;
-    const int grid1 = items1 < 2 * num_sms() ? items1 : 2 * num_sms();
-    STA_CHECK_CUDA(launch_pdl(attention_1q_kernel, dim3(grid1), dim3(ATT1_THREADS), ATT1_SMEM, stream, 1, tmQ, tmK, tmV, tmO, p,
-                              a.q_col0, a.k_col0, a.v_col0));
-    return 0;
+#define STA_ATTN_1Q_CASE(X2)                                                                                                \
+  if (feat == (AF_1Q | ((X2) ? AF_X2 : 0))) {                                                                               \
+    static PerDeviceOnce once;                                                                                              \
+    STA_CHECK_CUDA(once.run([&] {                                                                                           \
+      return cudaFuncSetAttribute(attention_1q_kernel<X2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT1_SMEM);    \
+    }));                                                                                                                    \
+    const int items1 = ((a.nq - split + 127) / 128) * a.heads * a.batch;                                                    \
+    const int grid1 = items1 < 2 * num_sms() ? items1 : 2 * num_sms();                                                      \
+    STA_CHECK_CUDA(launch_pdl(attention_1q_kernel<X2>, dim3(grid1), dim3(ATT1_THREADS), ATT1_SMEM, stream, 1, tmQ, tmK, tmV, \
+                              tmO, p, a.q_col0, a.k_col0, a.v_col0));                                                       \
+    return 0;                                                                                                               \
   }
+  STA_ATTN_1Q_CASE(false)
+  STA_ATTN_1Q_CASE(true)
+#undef STA_ATTN_1Q_CASE
   set_last_error("launch_attention: no kernel instance for this STA_ATTN_FEAT value");
   return 2;
 }

@@ -341,16 +341,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
   return d;
 }
 // Same layout with an arbitrary stride between the 8-row groups and a start address that is only 128-byte (one row)
-// aligned: bits [49,52) carry the "matrix base offset" = (start >> 7) & 7, the phase of the 128-byte swizzle pattern at
-// the start row (PTX ISA, tcgen05 shared-memory descriptor).  Used by the halo-staged 3x3 convolution, whose nine filter
-// taps are nine row-shifted views of ONE staged input tile.
-__device__ __forceinline__ uint64_t make_smem_desc_sw128_ex(uint32_t saddr, uint32_t sbo_bytes) {
+// aligned.  Used by the halo-staged 3x3 convolution, whose nine filter taps are nine row-shifted views of ONE staged input
+// tile.  MEASURED on B200 (tools/conv_ab.py, profiles/r02_conv_ab_2.log): the tensor core applies the 128-byte swizzle to the
+// ABSOLUTE shared-memory address bits (chunk bits [4,7) ^= row bits [7,10)), exactly as TMA wrote the tile, so a row-shifted
+// start needs NO "matrix base offset" (bits [49,52)); setting it to (start >> 7) & 7 shifts the pattern a second time and
+// gives wrong results for every tap with a column shift.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_rows(uint32_t saddr, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
   d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>((saddr >> 7) & 7) << 49;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
@@ -386,6 +387,27 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Packed fp32 pairs (sm_100: FFMA2 / FADD2 work on 64-bit register pairs at the rate of the scalar instructions).  The
+// attention softmax issues FFMA + EX2 + FADD + 1/2 F2FP per score: with scalar FFMA / FADD two co-resident warps reach
+// 10.3 clk per warp-level EX2, with the packed forms 8.15 (the MUFU pipe itself: 8.0; tools/probe/mufu_probe.cu).
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 // 2^x on the FMA / ALU pipes (no MUFU), for x <= ~100: x = n + f with n = round(x), f in [-0.5, 0.5];
 // 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, far below the bf16 rounding of the softmax
 // probabilities it feeds), 2^n by adding n to the exponent field.  Inputs below -126 (incl. -inf) give ~1e-38.
@@ -418,6 +440,25 @@ __device__ __forceinline__ float gelu_erf(float x) {
   q = fmaf(a, q, -1.1511993408203125f);
   q = fmaf(a, q, -0.9999947547912598f);
   return fmaf(-fabsf(x), ex2_approx(q), fmaxf(x, 0.0f));
+}
+
+// Two GELUs at once with the packed fp32 instructions (FFMA2): the polynomial is evaluated in n = -min(|x|, 6) (odd
+// coefficients change sign), and gelu(x) = max(x, 0) + n * 2^q(n).  Using the clamped n in the last product instead of -|x|
+// changes the result by at most (|x| - 6) * 1e-9.  13 instructions per pair instead of 22.
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const float n0 = fmaxf(-fabsf(x0), -6.0f), n1 = fmaxf(-fabsf(x1), -6.0f);
+  const uint64_t n = f32x2_pack(n0, n1);
+  uint64_t q = f32x2_fma(n, f32x2_pack(3.4195283660665154e-05f, 3.4195283660665154e-05f),
+                         f32x2_pack(0.0007779477164149284f, 0.0007779477164149284f));
+  q = f32x2_fma(n, q, f32x2_pack(0.008105806075036526f, 0.008105806075036526f));
+  q = f32x2_fma(n, q, f32x2_pack(0.053442906588315964f, 0.053442906588315964f));
+  q = f32x2_fma(n, q, f32x2_pack(-0.4587582051753998f, -0.4587582051753998f));
+  q = f32x2_fma(n, q, f32x2_pack(1.1511993408203125f, 1.1511993408203125f));
+  q = f32x2_fma(n, q, f32x2_pack(-0.9999947547912598f, -0.9999947547912598f));
+  float q0, q1;
+  f32x2_unpack(q, q0, q1);
+  const uint64_t r = f32x2_fma(n, f32x2_pack(ex2_approx(q0), ex2_approx(q1)), f32x2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+  f32x2_unpack(r, x0, x1);
 }
 
 __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {

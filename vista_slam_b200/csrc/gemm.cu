@@ -36,7 +36,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, long long slice_elems, i
 template <int BN, int AMODE, int EPI, int CG, int EW, bool TMA>
 static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        int num_tiles, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG, EW, EPI, TMA>;
+  using Cfg = GemmCfg<BN, CG, EW, EPI, TMA, AMODE == A_CONV3H>;
   auto kern = gemm_tc_kernel<BN, AMODE, EPI, CG, EW, TMA>;
   static PerDeviceOnce once;  // the opt-in is per device, not per process
   STA_CHECK_CUDA(once.run(
@@ -78,8 +78,10 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
 
   // TMA-store epilogue (epilogue_tile_tma) for the wide linear layers: bf16 / GELU / RoPE outputs without skip
   // tensors, fp32 outputs that either have no residual or accumulate in place (out += ..., bulk reduce-add).
-  static int tma_mode = -1, small_mode = -1;
+  static int tma_mode = -1, small_mode = -1, halo_mode = -1;
   if (tma_mode < 0) {
+    const char* eh = getenv("STA_CONV_HALO");  // 0: one TMA box per filter tap (A_CONV3) instead of the halo-staged tile (A/B)
+    halo_mode = (eh && eh[0] == '0') ? 0 : 1;
     const char* e = getenv("STA_GEMM_TMA_EPI");  // 0 disables (A/B timing and debugging)
     tma_mode = (e && e[0] == '0') ? 0 : 1;
     e = getenv("STA_GEMM_SMALL");  // 0 disables the small-problem route (A/B timing)
@@ -118,6 +120,7 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
       }
     }
   }
+  const int amode = (g.amode == A_CONV3 && halo_mode) ? A_CONV3H : g.amode;
   if (small_mode && g.amode == A_CONV3 && g.epi == EPI_BF16 && bn == 256) {
     // same for the DPT convolutions at low resolution (K = 9 * 256 streamed by a handful of CTA pairs otherwise)
     const int mt = p.nimg * ((p.H + 7) / 8) * ((p.W + 15) / 16);
@@ -131,13 +134,14 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
   if (g.amode == A_CONV3) {
     STA_REQUIRE(p.Cin % 64 == 0, "conv input channels must be a multiple of 64");
     STA_REQUIRE(p.K == 9 * p.Cin, "conv K must be 9*Cin");
-    p.tiles_h = (p.H + 7) / 8;
-    p.tiles_w = (p.W + 15) / 16;
+    const bool halo = amode == A_CONV3H;  // 16 x 8-pixel tiles fed from one 18 x 16-pixel box per channel chunk
+    p.tiles_h = halo ? (p.H + 15) / 16 : (p.H + 7) / 8;
+    p.tiles_w = halo ? (p.W + 7) / 8 : (p.W + 15) / 16;
     p.M = p.nimg * p.H * p.W;
     m_tiles = p.nimg * p.tiles_h * p.tiles_w;
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.nimg};
     uint64_t strides[3] = {(uint64_t)p.Cin * 2, (uint64_t)p.W * p.Cin * 2, (uint64_t)p.H * p.W * p.Cin * 2};
-    uint32_t box[4] = {64, 16, 8, 1};
+    uint32_t box[4] = {64, 16, halo ? 18u : 8u, 1};
     if (make_tmap_bf16(&tmA, g.A, 4, dims, strides, box)) return 1;
   } else {
     STA_REQUIRE(g.lda % 8 == 0, "lda must be a multiple of 8 elements (16 bytes)");
@@ -185,11 +189,19 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
 
   // 8 epilogue warps everywhere: with the TMA-store epilogue every fused epilogue of the trunk fits under the
   // K >= 768 mainloop, and the smaller CTA keeps a 5-deep operand ring (16 warps were measured slower end to end).
-  const int ew = 8;
+  // Exception: the DPT convolutions that add skip tensors and / or write a second (ReLU) copy are epilogue-bound with 8
+  // warps (tools/conv_ab.py): they get 16.  STA_CONV_EW16=0 disables (A/B timing).
+  static int ew16_mode = -1;
+  if (ew16_mode < 0) {
+    const char* e = getenv("STA_CONV_EW16");
+    ew16_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int ew =
+      (ew16_mode && cg == 2 && amode == A_CONV3H && bn == 256 && g.epi == EPI_BF16 && (p.resid != nullptr || p.out2 != nullptr)) ? 16 : 8;
 
   int rc = -1;
 #define STA_GEMM_CASE3(BN_, AM_, EP_, EW_, TMA_)                                                                  \
-  if (rc < 0 && bn == BN_ && g.amode == AM_ && g.epi == EP_ && ew == EW_ && tma == TMA_)                          \
+  if (rc < 0 && bn == BN_ && amode == AM_ && g.epi == EP_ && ew == EW_ && tma == TMA_)                            \
     rc = (cg == 2) ? launch_inst<BN_, AM_, EP_, 2, EW_, TMA_>(tmA, tmB, tmC, p, num_tiles, stream)                \
                    : launch_inst<BN_, AM_, EP_, 1, EW_, TMA_>(tmA, tmB, tmC, p, num_tiles, stream);
 #define STA_GEMM_CASE(BN_, AM_, EP_) STA_GEMM_CASE3(BN_, AM_, EP_, 8, false)
@@ -212,6 +224,11 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
   STA_GEMM_CASE(256, A_CONV3, EPI_BF16)
   STA_GEMM_CASE(128, A_CONV3, EPI_BF16)
   STA_GEMM_CASE(128, A_CONV3, EPI_HEAD)
+  STA_GEMM_CASE(256, A_CONV3H, EPI_BF16)
+  if (rc < 0 && ew == 16)  // CTA pair only (a single CTA has no room for 16 staging buffers beside the halo tiles)
+    rc = launch_inst<256, A_CONV3H, EPI_BF16, 2, 16, false>(tmA, tmB, tmC, p, num_tiles, stream);
+  STA_GEMM_CASE(128, A_CONV3H, EPI_BF16)
+  STA_GEMM_CASE(128, A_CONV3H, EPI_HEAD)
 #undef STA_GEMM_CASE
 #undef STA_GEMM_CASE3
   if (rc == 0 && ksplit > 1) {

@@ -19,7 +19,13 @@
 
 namespace sta {
 
-enum AMode : int { A_LINEAR = 0, A_CONV3 = 1 };
+// A_CONV3:  3x3 convolution, one TMA box (8 x 16 pixels x 64 channels, shifted by the tap) per filter tap and channel chunk.
+// A_CONV3H: 3x3 convolution, halo-staged: ONE box of 18 x 16 pixels x 64 channels per channel chunk feeds all nine taps --
+//           a tap is a row-shifted view of the staged tile (tile 16 rows x 8 pixels, 8-row descriptor groups 2048 bytes
+//           apart, descriptor base offset = the tap's column shift).  Shared-memory write traffic of the A operand drops from
+//           9 x 16 KB to 36 KB per channel chunk; the N = 128 head convolutions were bound by exactly that traffic.
+enum AMode : int { A_LINEAR = 0, A_CONV3 = 1, A_CONV3H = 2 };
+__host__ __device__ constexpr bool is_conv(int amode) { return amode != A_LINEAR; }
 enum Epi : int {
   EPI_BF16 = 0,     // out_bf16 = [relu](acc + bias [+ resid_bf16] [+ resid2_bf16]); optional relu copy in out2
   EPI_GELU = 1,     // out_bf16 = gelu_erf(acc + bias)
@@ -73,7 +79,7 @@ struct GemmParams {
 // TMA = true: the epilogue writes through shared memory + TMA tensor stores (epilogue_tile_tma), else the
 // transposing per-warp staging path (epilogue_tile).
 constexpr int kRopeLd = 36;  // floats per staged sin/cos table row (32 + 4 pad: conflict-free row-per-lane reads)
-template <int BN, int CG, int EW, int EPI, bool TMA>
+template <int BN, int CG, int EW, int EPI, bool TMA, bool HALO = false>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;
@@ -89,11 +95,17 @@ struct GemmCfg {
   static constexpr int ROPE_SMEM_ROWS = 64;  // positions -1 .. 62
   static constexpr uint32_t ROPE_SMEM_BYTES = (EPI == EPI_ROPE) ? ROPE_SMEM_ROWS * kRopeLd * sizeof(float) : 0;
   static constexpr uint32_t MAX_SMEM = 227 * 1024;
+  // halo-staged convolution (A_CONV3H): the ring holds B tiles only; two 18 x 16 x 64-channel input tiles besides it
+  static constexpr uint32_t HALO_BYTES = 18 * 16 * 128;
+  static constexpr int HALO_STAGES = 2;
+  static constexpr uint32_t HALO_TOTAL = HALO ? HALO_STAGES * HALO_BYTES : 0;
+  static constexpr uint32_t STAGE_BYTES = HALO ? B_BYTES : A_BYTES + B_BYTES;
   static constexpr int STAGES_FIT =
-      (MAX_SMEM - BAR_BYTES - EPI_SMEM_BYTES - STG_BYTES - ROPE_SMEM_BYTES) / (A_BYTES + B_BYTES);
+      (MAX_SMEM - BAR_BYTES - EPI_SMEM_BYTES - STG_BYTES - ROPE_SMEM_BYTES - HALO_TOTAL) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
-  // layout: operand ring | staging (1024-byte aligned) | barriers | EPI_HEAD partials | RoPE table
-  static constexpr uint32_t OFF_STG = STAGES * (A_BYTES + B_BYTES);
+  // layout: operand ring | halo tiles | staging (1024-byte aligned) | barriers | EPI_HEAD partials | RoPE table
+  static constexpr uint32_t OFF_HALO = STAGES * STAGE_BYTES;
+  static constexpr uint32_t OFF_STG = OFF_HALO + HALO_TOTAL;
   static constexpr uint32_t OFF_BAR = OFF_STG + STG_BYTES;
   static constexpr uint32_t OFF_EPI = OFF_BAR + BAR_BYTES;
   static constexpr uint32_t OFF_ROPE = OFF_EPI + EPI_SMEM_BYTES;
@@ -101,7 +113,7 @@ struct GemmCfg {
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int EPI_THREADS = 32 * EPI_WARPS;
   static_assert(STAGES <= 8 && STAGES >= 3, "barrier area holds at most 8 stages");
-  static_assert(OFF_STG % 1024 == 0 && STG_WARP_BYTES % 16 == 0, "staging alignment");
+  static_assert(OFF_STG % 1024 == 0 && OFF_HALO % 1024 == 0 && STG_WARP_BYTES % 16 == 0, "staging alignment");
 };
 
 // ---------------------------------------------------------------------------
@@ -129,6 +141,16 @@ __device__ __forceinline__ void tile_row(const GemmParams& p, int m_tile, int r_
     const int tw = t - th * p.tiles_w;
     const int h = th * 8 + (r_local >> 4);
     const int w = tw * 16 + (r_local & 15);
+    valid = (h < p.H) && (w < p.W) && (n < p.nimg);
+    orow = (static_cast<long long>(n) * p.H + h) * p.W + w;
+  } else if constexpr (AMODE == A_CONV3H) {  // 16 rows x 8 pixels per 128-row tile
+    const int tpi = p.tiles_h * p.tiles_w;
+    const int n = m_tile / tpi;
+    const int t = m_tile - n * tpi;
+    const int th = t / p.tiles_w;
+    const int tw = t - th * p.tiles_w;
+    const int h = th * 16 + (r_local >> 3);
+    const int w = tw * 8 + (r_local & 7);
     valid = (h < p.H) && (w < p.W) && (n < p.nimg);
     orow = (static_cast<long long>(n) * p.H + h) * p.W + w;
   } else {
@@ -522,7 +544,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     if (trace) trace[1 + 3 * c] = clock64();
     if constexpr (EPI == EPI_GELU) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+      for (int i = 0; i < 32; i += 2) gelu_erf2(v[i], v[i + 1]);
     }
     if constexpr (EPI == EPI_BF16) {
       if (p.relu_main) {
@@ -606,7 +628,8 @@ template <int BN, int AMODE, int EPI, int CG, int EW, bool TMA>
 __global__ void __launch_bounds__(GemmCfg<BN, CG, EW, EPI, TMA>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG, EW, EPI, TMA>;
+  constexpr bool HALO = (AMODE == A_CONV3H);
+  using Cfg = GemmCfg<BN, CG, EW, EPI, TMA, HALO>;
   static_assert(!TMA || (AMODE == A_LINEAR && (BN == 256 || BN == 128) &&
                          (EPI == EPI_BF16 || EPI == EPI_GELU || EPI == EPI_F32 || EPI == EPI_ROPE)),
                 "TMA-store epilogue: wide linear layers only");
@@ -616,13 +639,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint8_t* sB = smem + (HALO ? 0u : STAGES * A_BYTES);
+  [[maybe_unused]] uint8_t* sH = smem + Cfg::OFF_HALO;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  [[maybe_unused]] uint64_t* hfull = tempty + 2;   // halo tiles (A_CONV3H)
+  [[maybe_unused]] uint64_t* hempty = tempty + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 6);
+  static_assert((2 * STAGES + 10) * 8 + 4 <= Cfg::BAR_BYTES, "barrier area");
   [[maybe_unused]] float* epi_smem = reinterpret_cast<float*>(smem + Cfg::OFF_EPI);
   uint8_t* stg_all = smem + Cfg::OFF_STG;
   [[maybe_unused]] float* rope_s = reinterpret_cast<float*>(smem + Cfg::OFF_ROPE);
@@ -633,13 +660,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const bool leader = (cta_rank == 0);
 
   // 128-row tiles; a work item covers CG consecutive ones
-  const int m_tiles128 = (AMODE == A_CONV3) ? p.nimg * p.tiles_h * p.tiles_w : (p.M + 127) / 128;
+  const int m_tiles128 = is_conv(AMODE) ? p.nimg * p.tiles_h * p.tiles_w : (p.M + 127) / 128;
   const int m_tiles = (m_tiles128 + CG - 1) / CG;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int ksplit = TMA ? p.ksplit : 1;
   const int num_tiles = m_tiles * n_tiles * ksplit;  // work items (m, n, ks), ks fastest
-  const int cpb = (AMODE == A_CONV3) ? (p.Cin / 64) : 1;  // 64-channel chunks per filter tap
-  const int nkb = (AMODE == A_CONV3) ? 9 * cpb : (p.K + 63) / 64;
+  const int cpb = is_conv(AMODE) ? (p.Cin / 64) : 1;  // 64-channel chunks per filter tap
+  const int nkb = is_conv(AMODE) ? 9 * cpb : (p.K + 63) / 64;
   const int first_tile = blockIdx.x / CG;
   const int tile_step = gridDim.x / CG;
 
@@ -653,6 +680,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(&tfull[1], 1);
     mbar_init(&tempty[0], Cfg::EPI_WARPS * CG);  // every epilogue warp of the pair arrives on the leader's barrier
     mbar_init(&tempty[1], Cfg::EPI_WARPS * CG);
+    if constexpr (HALO) {
+      for (int s = 0; s < Cfg::HALO_STAGES; ++s) {
+        mbar_init(&hfull[s], 1);
+        mbar_init(&hempty[s], 1);
+      }
+    }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -693,6 +726,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      [[maybe_unused]] int hstage = 0;
+      [[maybe_unused]] uint32_t hphase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int ks = tile % ksplit, mn = tile / ksplit;
         const int m_tile = (mn / n_tiles) * CG + static_cast<int>(cta_rank);  // this CTA's 128-row tile
@@ -700,14 +735,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb0 = ks * nkb / ksplit, kb1 = (ks + 1) * nkb / ksplit;
         const int b_row0 = n_tile * BN + static_cast<int>(cta_rank) * (BN / CG);
         int cn = 0, ch0 = 0, cw0 = 0;
-        if constexpr (AMODE == A_CONV3) {
+        if constexpr (is_conv(AMODE)) {
           const int tpi = p.tiles_h * p.tiles_w;
           cn = m_tile / tpi;  // >= nimg for the padding tile of an odd tile count: TMA zero-fills
           const int t = m_tile - cn * tpi;
           const int th = t / p.tiles_w;
-          ch0 = th * 8;
-          cw0 = (t - th * p.tiles_w) * 16;
+          ch0 = th * (HALO ? 16 : 8);
+          cw0 = (t - th * p.tiles_w) * (HALO ? 8 : 16);
         }
+        if constexpr (HALO) {
+          // channel chunk outermost: one halo tile, then the nine taps' weight tiles
+          for (int cc = 0; cc < cpb; ++cc) {
+            mbar_wait(&hempty[hstage], hphase ^ 1);
+            if (CG == 1 || leader) mbar_arrive_expect_tx(&hfull[hstage], CG * Cfg::HALO_BYTES);
+            if constexpr (CG == 2)
+              tma_load_4d_cg2(sH + hstage * Cfg::HALO_BYTES, &tmA, &hfull[hstage], cc * 64, cw0 - 1, ch0 - 1, cn);
+            else
+              tma_load_4d(sH + hstage * Cfg::HALO_BYTES, &tmA, &hfull[hstage], cc * 64, cw0 - 1, ch0 - 1, cn);
+            if (++hstage == Cfg::HALO_STAGES) { hstage = 0; hphase ^= 1; }
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              if (CG == 1 || leader) mbar_arrive_expect_tx(&full[stage], CG * B_BYTES);
+              if constexpr (CG == 2)
+                tma_load_2d_cg2(sB + stage * B_BYTES, &tmB, &full[stage], (tap * cpb + cc) * 64, b_row0);
+              else
+                tma_load_2d(sB + stage * B_BYTES, &tmB, &full[stage], (tap * cpb + cc) * 64, b_row0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else {
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (CG == 1 || leader) mbar_arrive_expect_tx(&full[stage], CG * (A_BYTES + B_BYTES));
@@ -732,6 +788,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d(sB + stage * B_BYTES, &tmB, &full[stage], kb * 64, b_row0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        }
       }
     }
   } else if (warp == 1) {
@@ -740,6 +797,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = make_idesc_bf16(128 * CG, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
+      [[maybe_unused]] int hstage = 0;
+      [[maybe_unused]] uint32_t hphase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
@@ -752,6 +811,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t d_tmem = tmem_base + acc * BN;
         const int ks = tile % ksplit;
         const int kb0 = ks * nkb / ksplit, kb1 = (ks + 1) * nkb / ksplit;
+        if constexpr (HALO) {
+          for (int cc = 0; cc < cpb; ++cc) {
+            mbar_wait(&hfull[hstage], hphase);
+            const uint32_t hbase = smem_u32(sH + hstage * Cfg::HALO_BYTES);
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&full[stage], phase);
+              tc_fence_after();
+              const int kh = tap / 3, kw = tap - kh * 3;
+              // output pixel (y, x) of the 16 x 8 tile reads halo pixel (y + kh, x + kw); halo rows are 16 pixels = 2048 B
+              const uint64_t adesc = make_smem_desc_sw128_rows(hbase + (kh * 16 + kw) * 128, 2048);
+              const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * B_BYTES));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if constexpr (CG == 2)
+                  umma_bf16_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cc > 0 || tap > 0 || k != 0) ? 1u : 0u);
+                else
+                  umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cc > 0 || tap > 0 || k != 0) ? 1u : 0u);
+              }
+              if constexpr (CG == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if constexpr (CG == 2) umma_commit_cg2(&hempty[hstage]); else umma_commit(&hempty[hstage]);
+            if (++hstage == Cfg::HALO_STAGES) { hstage = 0; hphase ^= 1; }
+          }
+        } else {
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -767,6 +851,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if constexpr (CG == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
         }
         if constexpr (CG == 2) umma_commit_cg2(&tfull[acc]); else umma_commit(&tfull[acc]);
         if (trc) p.dbg[256 + 4 * tcount + 2] = clock64();
