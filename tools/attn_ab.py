@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
-FEATS = [16, 144, 64, 192]
+FEATS = [16, 144, 192]
 REF_LIB = os.path.join(ROOT, "tools", "ab", "libsta_r01attn.so")  # optional: a build with the round-1 attention kernel
 
 

@@ -27,6 +27,8 @@
 // exp2 (MUFU-bound) phase overlaps the other's load / max / store phases.
 #include "common.cuh"
 #include "host_util.h"
+
+#include <stdio.h>
 #include "ops.h"
 
 #include <stdlib.h>
@@ -71,7 +73,13 @@ struct AttnParams {
   float scale_log2;
   __nv_bfloat16* out;
   long long ldo;
+  long long* dbg;  // clock64 stamps of CTA 0 (only in builds with -DSTA_ATTN_TRACE_BUILD; tools/attn_trace.py), else unused
 };
+#ifdef STA_ATTN_TRACE_BUILD
+#define ATTN_STAMP(cond, idx) do { if ((cond) && p.dbg) p.dbg[(idx)] = clock64(); } while (0)
+#else
+#define ATTN_STAMP(cond, idx) do { } while (0)
+#endif
 
 template <int FEAT>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -705,12 +713,17 @@ attention_1q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         int v_st = 0, j = 0;
         uint32_t v_ph = 0;
         for (int n = 0; n < total; ++n) {
+          ATTN_STAMP(blockIdx.x == 0 && n < 24, 8 * n + 0);
           if (n + 1 < total) {  // S(n+1) as soon as the softmax threads hold S(n) in registers
             mbar_wait(s_free, n & 1);
+            ATTN_STAMP(blockIdx.x == 0 && n < 24, 8 * n + 1);
             issue_s();
           }
+          ATTN_STAMP(blockIdx.x == 0 && n < 24, 8 * n + 2);
           mbar_wait(p_full, n & 1);
+          ATTN_STAMP(blockIdx.x == 0 && n < 24, 8 * n + 3);
           mbar_wait(&v_full[v_st], v_ph);
+          ATTN_STAMP(blockIdx.x == 0 && n < 24, 8 * n + 4);
           tc_fence_after();
           const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + v_st * TILE_BYTES));
           const int ksteps = (narrow_tail && j == T - 1) ? 1 : 8;
@@ -718,6 +731,7 @@ attention_1q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             umma_bf16_ts(tmem_base + 128, tmem_base + 192 + 8 * k, vdesc + (2048 >> 4) * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
           umma_commit(&v_empty[v_st]);
           umma_commit(o_full);
+          ATTN_STAMP(blockIdx.x == 0 && n < 24, 8 * n + 5);
           if (++v_st == KV1_STAGES) { v_st = 0; v_ph ^= 1; }
           if (++j == T) j = 0;
         }
@@ -743,7 +757,10 @@ attention_1q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       float l = 0.f;
       for (int j = 0; j < T; ++j, ++n) {
         const int nvalid = p.nk - j * 128;  // >= 1
+        [[maybe_unused]] const bool trc = blockIdx.x == 0 && threadIdx.x == 128 && n < 24;
+        ATTN_STAMP(trc, 256 + 8 * n + 0);
         mbar_wait(s_full, n & 1);
+        ATTN_STAMP(trc, 256 + 8 * n + 1);
         tc_fence_after();
         if (nvalid <= 16 && j == T - 1) {
           // ---- narrow tail tile: S is 128 x 16, P V uses a single 16-key step ----
@@ -829,6 +846,7 @@ attention_1q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
         }
         const float m_true = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+        ATTN_STAMP(trc, 256 + 8 * n + 2);
         // lazy rescaling: keep the old reference maximum unless the row maximum grew by more than 2^8
         const bool raise = m_true > m_used + kRescaleThreshold;  // always true on the first tile (m_used = -inf)
         const float m_new = raise ? m_true : m_used;
@@ -851,6 +869,7 @@ attention_1q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
           }
         }
+        ATTN_STAMP(trc, 256 + 8 * n + 3);
         // ---- P = exp2(S*c - m_used) -> packed bf16 -> tensor memory (64 keys per tcgen05.st) ----
         float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
         [[maybe_unused]] uint64_t rsA = 0, rsB = 0;  // X2: two packed pairs of row-sum partials
@@ -890,10 +909,12 @@ attention_1q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           f32x2_unpack(rsB, rs2, rs3);
         }
         l += (rs0 + rs1) + (rs2 + rs3);
+        ATTN_STAMP(trc, 256 + 8 * n + 5);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
+        ATTN_STAMP(trc, 256 + 8 * n + 6);
       }
       // ---- item epilogue: O / l -> bf16 -> 128B-swizzled staging tile -> one TMA store ----
       mbar_wait(o_full, (n - 1) & 1);
@@ -1204,6 +1225,10 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   p.out = a.out;
   p.ldo = a.ldo;
   p.heads = a.heads;
+  {
+    const char* e = getenv("STA_ATTN_TRACE");
+    p.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+  }
   const size_t row0_smem = (((a.nk + 3) & ~3) + 16 + 32 * 64) * sizeof(float);
   static int pingpong_env = -1, feat_env = -2;
   if (pingpong_env < 0) {
@@ -1265,10 +1290,23 @@ int launch_attention(const AttnLaunch& a, cudaStream_t stream) {
   if (feat == (AF_1Q | ((X2) ? AF_X2 : 0))) {                                                                               \
     static PerDeviceOnce once;                                                                                              \
     STA_CHECK_CUDA(once.run([&] {                                                                                           \
-      return cudaFuncSetAttribute(attention_1q_kernel<X2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT1_SMEM);    \
+      cudaError_t e =                                                                                                       \
+          cudaFuncSetAttribute(attention_1q_kernel<X2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT1_SMEM);       \
+      if (e != cudaSuccess) return e;                                                                                       \
+      /* two CTAs per SM need the full 228 KB shared-memory carve-out */                                                    \
+      e = cudaFuncSetAttribute(attention_1q_kernel<X2>, cudaFuncAttributePreferredSharedMemoryCarveout,                     \
+                               (int)cudaSharedmemCarveoutMaxShared);                                                        \
+      if (e != cudaSuccess) return e;                                                                                       \
+      if (getenv("STA_ATTN_DEBUG")) {                                                                                       \
+        int nb = -1;                                                                                                        \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attention_1q_kernel<X2>, ATT1_THREADS, ATT1_SMEM);               \
+        fprintf(stderr, "attention_1q_kernel<%d>: %d resident CTAs per SM (occupancy API)\n", (int)(X2), nb);               \
+      }                                                                                                                     \
+      return cudaSuccess;                                                                                                   \
     }));                                                                                                                    \
     const int items1 = ((a.nq - split + 127) / 128) * a.heads * a.batch;                                                    \
-    const int grid1 = items1 < 2 * num_sms() ? items1 : 2 * num_sms();                                                      \
+    static const int ctas_per_sm = (getenv("STA_ATTN_1Q_CTAS") && getenv("STA_ATTN_1Q_CTAS")[0] == '1') ? 1 : 2; /* A/B */    \
+    const int grid1 = items1 < ctas_per_sm * num_sms() ? items1 : ctas_per_sm * num_sms();                                  \
     STA_CHECK_CUDA(launch_pdl(attention_1q_kernel<X2>, dim3(grid1), dim3(ATT1_THREADS), ATT1_SMEM, stream, 1, tmQ, tmK, tmV, \
                               tmO, p, a.q_col0, a.k_col0, a.v_col0));                                                       \
     return 0;                                                                                                               \
