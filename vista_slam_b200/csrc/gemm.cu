@@ -141,7 +141,7 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
     m_tiles = p.nimg * p.tiles_h * p.tiles_w;
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.nimg};
     uint64_t strides[3] = {(uint64_t)p.Cin * 2, (uint64_t)p.W * p.Cin * 2, (uint64_t)p.H * p.W * p.Cin * 2};
-    uint32_t box[4] = {64, 16, halo ? 18u : 8u, 1};
+    uint32_t box[4] = {64, halo ? (uint32_t)kHaloPitch : 16u, halo ? 18u : 8u, 1};
     if (make_tmap_bf16(&tmA, g.A, 4, dims, strides, box)) return 1;
   } else {
     STA_REQUIRE(g.lda % 8 == 0, "lda must be a multiple of 8 elements (16 bytes)");

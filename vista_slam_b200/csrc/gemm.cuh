@@ -78,6 +78,10 @@ struct GemmParams {
 //         128 rows of A and BN/2 rows of B, so per-SM shared-memory traffic per MMA is halved for B.
 // TMA = true: the epilogue writes through shared memory + TMA tensor stores (epilogue_tile_tma), else the
 // transposing per-warp staging path (epilogue_tile).
+// A_CONV3H: pixels per staged halo row.  10 = the 8-pixel tile plus its two halo columns (dense box, 8-row descriptor groups
+// 1280 B apart -- groups then start at any 128-byte multiple, which the absolute-address swizzle permits); 16 = padded rows
+// (groups 2048 B apart), 60 % more bytes per box.
+constexpr int kHaloPitch = 10;
 constexpr int kRopeLd = 36;  // floats per staged sin/cos table row (32 + 4 pad: conflict-free row-per-lane reads)
 template <int BN, int CG, int EW, int EPI, bool TMA, bool HALO = false>
 struct GemmCfg {
@@ -96,8 +100,9 @@ struct GemmCfg {
   static constexpr uint32_t ROPE_SMEM_BYTES = (EPI == EPI_ROPE) ? ROPE_SMEM_ROWS * kRopeLd * sizeof(float) : 0;
   static constexpr uint32_t MAX_SMEM = 227 * 1024;
   // halo-staged convolution (A_CONV3H): the ring holds B tiles only; two 18 x 16 x 64-channel input tiles besides it
-  static constexpr uint32_t HALO_BYTES = 18 * 16 * 128;
-  static constexpr int HALO_STAGES = 2;
+  static constexpr uint32_t HALO_TX_BYTES = 18 * kHaloPitch * 128;                 // bytes one box delivers
+  static constexpr uint32_t HALO_BYTES = (HALO_TX_BYTES + 1023u) & ~1023u;        // stage stride (swizzle-pattern aligned)
+  static constexpr int HALO_STAGES = kHaloPitch == 16 ? 2 : 3;
   static constexpr uint32_t HALO_TOTAL = HALO ? HALO_STAGES * HALO_BYTES : 0;
   static constexpr uint32_t STAGE_BYTES = HALO ? B_BYTES : A_BYTES + B_BYTES;
   static constexpr int STAGES_FIT =
@@ -646,10 +651,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = tfull + 2;
-  [[maybe_unused]] uint64_t* hfull = tempty + 2;   // halo tiles (A_CONV3H)
-  [[maybe_unused]] uint64_t* hempty = tempty + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 6);
-  static_assert((2 * STAGES + 10) * 8 + 4 <= Cfg::BAR_BYTES, "barrier area");
+  [[maybe_unused]] uint64_t* hfull = tempty + 2;   // halo tiles (A_CONV3H), up to 3 stages
+  [[maybe_unused]] uint64_t* hempty = tempty + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 8);
+  static_assert(Cfg::HALO_STAGES <= 3 && (2 * STAGES + 12) * 8 + 4 <= Cfg::BAR_BYTES, "barrier area");
   [[maybe_unused]] float* epi_smem = reinterpret_cast<float*>(smem + Cfg::OFF_EPI);
   uint8_t* stg_all = smem + Cfg::OFF_STG;
   [[maybe_unused]] float* rope_s = reinterpret_cast<float*>(smem + Cfg::OFF_ROPE);
@@ -747,7 +752,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // channel chunk outermost: one halo tile, then the nine taps' weight tiles
           for (int cc = 0; cc < cpb; ++cc) {
             mbar_wait(&hempty[hstage], hphase ^ 1);
-            if (CG == 1 || leader) mbar_arrive_expect_tx(&hfull[hstage], CG * Cfg::HALO_BYTES);
+            if (CG == 1 || leader) mbar_arrive_expect_tx(&hfull[hstage], CG * Cfg::HALO_TX_BYTES);
             if constexpr (CG == 2)
               tma_load_4d_cg2(sH + hstage * Cfg::HALO_BYTES, &tmA, &hfull[hstage], cc * 64, cw0 - 1, ch0 - 1, cn);
             else
@@ -819,8 +824,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               mbar_wait(&full[stage], phase);
               tc_fence_after();
               const int kh = tap / 3, kw = tap - kh * 3;
-              // output pixel (y, x) of the 16 x 8 tile reads halo pixel (y + kh, x + kw); halo rows are 16 pixels = 2048 B
-              const uint64_t adesc = make_smem_desc_sw128_rows(hbase + (kh * 16 + kw) * 128, 2048);
+              // output pixel (y, x) of the 16 x 8 tile reads halo pixel (y + kh, x + kw); halo rows are kHaloPitch pixels
+              const uint64_t adesc = make_smem_desc_sw128_rows(hbase + (kh * kHaloPitch + kw) * 128, kHaloPitch * 128);
               const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * B_BYTES));
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
