@@ -46,7 +46,7 @@ def test_attention_self_and_cross(capsys):
 
 
 def test_bandwidth_kernels(capsys):
-    assert len(_collect(bu.group_misc, capsys)) == 11
+    assert len(_collect(bu.group_misc, capsys)) == 15
 
 
 def test_split_precision_mode_of_the_tensor_core_kernels(capsys):

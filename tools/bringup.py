@@ -326,6 +326,12 @@ def group_misc():
     check(L.sta_op_upsample2x(ptr(x), ptr(o), 2, 7, 9, 64, st))
     ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True)
     report("upsample2x align_corners", o, ref.permute(0, 2, 3, 1), 1e-2)
+    for (nimg, H, W, C) in [(1, 12, 16, 256), (3, 5, 3, 128), (2, 24, 32, 128), (1, 1, 40, 64)]:
+        x = torch.randn(nimg, H, W, C, device=dev).bfloat16()
+        o = torch.zeros(nimg, 2 * H, 2 * W, C, device=dev, dtype=torch.bfloat16)
+        check(L.sta_op_upsample2x(ptr(x), ptr(o), nimg, H, W, C, st))
+        ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True)
+        report("upsample2x %dx%dx%dx%d" % (nimg, H, W, C), o, ref.permute(0, 2, 3, 1), 1e-2)
     # im2col s2
     x = torch.randn(2, 7, 10, 64, device=dev).bfloat16()
     o = torch.zeros(2 * 4 * 5, 9 * 64, device=dev, dtype=torch.bfloat16)
