@@ -34,7 +34,7 @@ def test_gemm_shapes_and_tails(capsys):
 
 def test_gemm_fused_epilogues(capsys):
     # gelu, residual x2 + relu copy, relu, BN=128 path, fp32 (in-place reduce-add, plain, separate residual), row map, RoPE, ConvT
-    assert len(_collect(bu.group_gemm_epi, capsys)) == 19
+    assert len(_collect(bu.group_gemm_epi, capsys)) == 20
 
 
 def test_implicit_gemm_conv_and_head(capsys):
@@ -95,6 +95,7 @@ def test_error_reporting_through_the_abi():
 @pytest.mark.parametrize("env,group", [
     ({"STA_CONV_HALO": "0"}, "conv"),        # one TMA box per filter tap instead of the halo-staged tile
     ({"STA_CONV_EW16": "0"}, "conv"),        # 8 epilogue warps for the skip-tensor convolutions
+    ({"STA_GEMM_TAIL": "0"}, "gemm_epi"),    # full tiles in the last (partial) wave instead of half tiles
     ({"STA_ATTN_FEAT": "144"}, "attention"),  # query-tile-pair kernel for every shape
     ({"STA_ATTN_FEAT": "192"}, "attention"),  # one-query-tile-per-CTA kernel for every shape
     ({"STA_ATTN_FEAT": "16"}, "attention"),   # scalar FFMA / FADD softmax (A/B reference of the packed fp32 form)

@@ -187,6 +187,15 @@ def group_gemm_epi():
     xw0 = xw.clone()
     run_gemm(gemm_desc(epi=EPI_F32, A=Aw, lda=Kw, W=Ww, ldw=Kw, M=Mw, N=1024, K=Kw, bias=bl, out=xw, ldo=1024, resid=xw))
     report("wide M5000 f32 in place (reduce-add)", xw, xw0 + refw, 2e-3)
+    # wave-quantisation tail: 24576 x 1024 = 384 tile pairs on 74 CTA pairs -> the last 14 run as 28 half tiles (256 x 128)
+    Mt, Kt = 24576, 256
+    At = torch.randn(Mt, Kt, device=dev).bfloat16()
+    Wt = (torch.randn(1024, Kt, device=dev) / math.sqrt(Kt)).bfloat16()
+    bt = torch.randn(1024, device=dev)
+    xt = torch.randn(Mt, 1024, device=dev)
+    xt0 = xt.clone()
+    run_gemm(gemm_desc(epi=EPI_F32, A=At, lda=Kt, W=Wt, ldw=Kt, M=Mt, N=1024, K=Kt, bias=bt, out=xt, ldo=1024, resid=xt))
+    report("M24576 N1024 f32 in place (half-tile tail wave)", xt, xt0 + At.float() @ Wt.float().t() + bt, 2e-3)
     # PIXSHUF: tokens (2 img, 5x7 grid), Cin 128, cout 64, k 2
     nimg, h, w, cin, cout, k = 2, 5, 7, 128, 64, 2
     At = torch.randn(nimg * h * w, cin, device=dev).bfloat16()

@@ -34,8 +34,9 @@ splitk_reduce_kernel(const float* __restrict__ partial, long long slice_elems, i
 }
 
 template <int BN, int AMODE, int EPI, int CG, int EW, bool TMA>
-static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p_in,
                        int num_tiles, cudaStream_t stream) {
+  GemmParams p = p_in;
   using Cfg = GemmCfg<BN, CG, EW, EPI, TMA, AMODE == A_CONV3H>;
   auto kern = gemm_tc_kernel<BN, AMODE, EPI, CG, EW, TMA>;
   static PerDeviceOnce once;  // the opt-in is per device, not per process
@@ -45,6 +46,24 @@ static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int max_items = num_sms() / CG;
   const int items = num_tiles < max_items ? num_tiles : max_items;
   if (items < 1) return 0;
+  // Wave-quantisation tail: with W work slots, num_tiles = k W + r leaves r tiles for a last, mostly idle wave (the
+  // encoder's N = 1024 layers: 384 tiles on 74 CTA pairs = 5 waves + 14 tiles).  If 2 r <= W those r tiles are issued as
+  // 2 r half tiles (256 x 128) instead: the last wave then takes half as long.  Same K order per output element, so the
+  // results are bit-identical to the full-tile schedule.  STA_GEMM_TAIL=0 disables (A/B timing).
+  p.tail_r = 0;
+  p.tail_first = num_tiles;
+  if (TMA && CG == 2 && BN == 256 && EPI == EPI_F32 && p.ksplit == 1 && num_tiles > items) {
+    static int tail_mode = -1;
+    if (tail_mode < 0) {
+      const char* e = getenv("STA_GEMM_TAIL");
+      tail_mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    const int r = num_tiles % items;
+    if (tail_mode && r > 0 && 2 * r <= items) {
+      p.tail_r = r;
+      p.tail_first = num_tiles - r;
+    }
+  }
   STA_CHECK_CUDA(launch_pdl(kern, dim3(items * CG), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, CG, tmA, tmB, tmC, p));
   return 0;
 }

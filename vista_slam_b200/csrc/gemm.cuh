@@ -70,6 +70,10 @@ struct GemmParams {
   // (K here is the physical 3K); bf16 outputs / bf16 skip tensors use the (hi | lo | hi) row layout with logical
   // width N (ldo = 3N).  fp32 outputs are unaffected.
   int split;
+  // Wave-quantisation tail (TMA epilogue, CTA pair, BN = 256, EPI_F32, no split-K): the last tail_r work items, which would
+  // run as a partial wave on a few CTA pairs, are each issued as TWO 256 x 128 half tiles (see launch_gemm).
+  int tail_first;  // first tile index of the tail
+  int tail_r;      // number of tail tiles (0 = off)
   long long* dbg;       // optional clock64 trace (env STA_GEMM_TRACE), else null
 };
 
@@ -477,19 +481,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
 // ---------------------------------------------------------------------------
 template <int BN, int EPI, int EW, typename Release>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmC, uint32_t taddr, int m_tile,
-                                                  int n_tile, int row_off, int quarter, int part, uint8_t* cbuf,
+                                                  int colbase, int nch, int row_off, int quarter, int part, uint8_t* cbuf,
                                                   const float* rope_s,
                                                   uint64_t* tfull_bar, uint32_t tfull_phase, Release&& release,
                                                   long long* trace) {
   constexpr int PARTS = EW / 4;
-  constexpr int CH = BN / PARTS;  // columns per epilogue warp
-  constexpr int NCH = CH / 32;    // 32-column TMEM loads per tile
+  constexpr int CH = BN / PARTS;  // columns per epilogue warp of a full tile
+  constexpr int NCH = CH / 32;    // 32-column TMEM loads per full tile; nch <= NCH is what this tile has (half tiles: NCH / 2)
   // 8 warps (168 registers): the next chunk's TMEM load is in flight while the current one is processed;
   // 16 warps (96 registers) rely on the four warps per scheduler instead
   constexpr bool PF = (EW == 8);
   constexpr bool OUT_F32 = (EPI == EPI_F32);
   const int lane = threadIdx.x & 31;
-  const int colbase = n_tile * BN + part * CH;
+  (void)part;
   const int row0 = m_tile * 128 + quarter * 32;  // first row of this warp's box (token index)
   const int srow0 = row0 + row_off;              // ... in the output tensor (split-K partial slices)
   const uint32_t cb = smem_u32(cbuf);
@@ -530,6 +534,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   tmem_ld32(taddr, acc[0]);
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
+    if (c >= nch) break;
     tmem_ld_wait();
     float* v = reinterpret_cast<float*>(acc[PF ? (c & 1) : 0]);
     const int col = colbase + c * 32;
@@ -537,7 +542,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     for (int j = 0; j < 8; ++j) {
       v[4 * j] += bcur[j].x; v[4 * j + 1] += bcur[j].y; v[4 * j + 2] += bcur[j].z; v[4 * j + 3] += bcur[j].w;
     }
-    if (c + 1 < NCH) {
+    if (c + 1 < nch) {
       if constexpr (PF) tmem_ld32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
       if (has_bias) {
 #pragma unroll
@@ -622,7 +627,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
       }
     }
     if constexpr (!PF) {
-      if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, acc[0]);  // the registers are free again
+      if (c + 1 < nch) tmem_ld32(taddr + (c + 1) * 32, acc[0]);  // the registers are free again
     }
     if (trace) trace[3 + 3 * c] = clock64();
   }
@@ -674,6 +679,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int nkb = is_conv(AMODE) ? 9 * cpb : (p.K + 63) / 64;
   const int first_tile = blockIdx.x / CG;
   const int tile_step = gridDim.x / CG;
+  // work items: tiles [0, num_tiles), the last tail_r of them as two half tiles each (TMA epilogue / CTA pair / BN = 256 only)
+  constexpr bool TAIL = TMA && CG == 2 && BN == 256 && EPI == EPI_F32;
+  const int tail_r = TAIL ? p.tail_r : 0;
+  const int num_work = num_tiles + tail_r;
+  auto work_tile = [&](int w, int& half) {
+    half = -1;
+    if (TAIL && tail_r > 0 && w >= p.tail_first) {
+      const int q = w - p.tail_first;
+      half = q & 1;
+      return p.tail_first + (q >> 1);
+    }
+    return w;
+  };
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) device_fatal("dynamic shared memory is not 1024-byte aligned");
@@ -733,12 +751,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       [[maybe_unused]] int hstage = 0;
       [[maybe_unused]] uint32_t hphase = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      for (int w = first_tile; w < num_work; w += tile_step) {
+        int half;
+        const int tile = work_tile(w, half);
         const int ks = tile % ksplit, mn = tile / ksplit;
         const int m_tile = (mn / n_tiles) * CG + static_cast<int>(cta_rank);  // this CTA's 128-row tile
         const int n_tile = mn % n_tiles;
         const int kb0 = ks * nkb / ksplit, kb1 = (ks + 1) * nkb / ksplit;
-        const int b_row0 = n_tile * BN + static_cast<int>(cta_rank) * (BN / CG);
+        // half tile: this CTA's 64 weight rows are the first 64 of the (full-size) box it loads
+        const int b_row0 = (half < 0) ? n_tile * BN + static_cast<int>(cta_rank) * (BN / CG)
+                                      : n_tile * BN + half * (BN / 2) + static_cast<int>(cta_rank) * (BN / 4);
         int cn = 0, ch0 = 0, cw0 = 0;
         if constexpr (is_conv(AMODE)) {
           const int tpi = p.tiles_h * p.tiles_w;
@@ -806,8 +828,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       [[maybe_unused]] uint32_t hphase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-        const int tcount = (tile - first_tile) / tile_step;
+      for (int w = first_tile; w < num_work; w += tile_step) {
+        int half;
+        const int tile = work_tile(w, half);
+        const uint32_t idesc_t = (half < 0) ? idesc : make_idesc_bf16(128 * CG, BN / 2, 0, 0);
+        const int tcount = (w - first_tile) / tile_step;
         const bool trc = p.dbg && blockIdx.x == 0 && tcount < 40;
         if (trc) p.dbg[256 + 4 * tcount + 0] = clock64();
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -850,9 +875,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < 4; ++k) {
             // advance 16 K-elements = 32 bytes inside the 128B swizzle atom (encoded >> 4)
             if constexpr (CG == 2)
-              umma_bf16_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+              umma_bf16_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_t, (kb > kb0 || k != 0) ? 1u : 0u);
             else
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_t, (kb > kb0 || k != 0) ? 1u : 0u);
           }
           if constexpr (CG == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -870,15 +895,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int part = (warp - 4) >> 2;  // which quarter of the tile's columns
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+    for (int w = first_tile; w < num_work; w += tile_step) {
+      int half;
+      const int tile = work_tile(w, half);
       const int ks = tile % ksplit, mn = tile / ksplit;
       const int m_tile = (mn / n_tiles) * CG + static_cast<int>(cta_rank);
       const int n_tile = mn % n_tiles;
-      const int tcount = (tile - first_tile) / tile_step;
+      const int tcount = (w - first_tile) / tile_step;
       const bool trc = p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && tcount < 40;
       if (trc) p.dbg[4 * tcount + 0] = clock64();
       if (trc) p.dbg[4 * tcount + 1] = clock64();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + part * (BN / Cfg::PARTS);
+      // columns of this epilogue warp: a quarter-of-the-parts slice of the full tile, or of the 128-column half tile
+      const int cols_w = (half < 0 ? BN : BN / 2) / Cfg::PARTS;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + part * cols_w;
       // hand the accumulator stage back to the MMA warp (called once all of this warp's TMEM loads have landed)
       auto release = [&]() {
         tc_fence_before();
@@ -888,7 +917,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
       if constexpr (TMA) {
-        epilogue_tile_tma<BN, EPI, EW>(p, &tmC, taddr, m_tile, n_tile, ks * p.split_rows, quarter, part,
+        epilogue_tile_tma<BN, EPI, EW>(p, &tmC, taddr, m_tile, n_tile * BN + (half < 0 ? 0 : half * (BN / 2)) + part * cols_w,
+                                       cols_w / 32, ks * p.split_rows, quarter, part,
                                        stg_all + (warp - 4) * Cfg::STG_WARP_BYTES, rope_s, &tfull[acc], acc_phase, release,
                                        (trc && tcount < 16) ? p.dbg + 512 + 16 * tcount : nullptr);
       } else {
